@@ -1,0 +1,116 @@
+// Dense contractions D = A * B^T of the GNNGP path and their fused epilogues (K2, K4, K5, K6,
+// initial kernels).  Dispatches between the tcgen05 3xTF32 engine (gemm_tc.cuh) and the fp32
+// CUDA-core tiles (gemm_simt.cuh); see gnngp_set_gemm_engine.
+#include <algorithm>
+#include <atomic>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace gnngp {
+
+extern std::atomic<int> g_gemm_engine;
+
+static bool use_tensor_cores(int64_t M, int64_t N, int64_t K)
+{
+    const int engine = g_gemm_engine.load();
+    if (engine == 0 || K <= 0) return false;
+    if (engine == 1) return true;
+    // auto: enough 128x256 tiles to occupy a good part of the chip and a K loop worth pipelining
+    return ceil_div(M, tc::BM) * ceil_div(N, tc::BN) >= 32 && K >= 128;
+}
+
+template <class Epi>
+static int contract(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                    const Epi &epi, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (use_tensor_cores(M, N, K)) return tc::gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, ws, ws_bytes, st);
+    return gemm_nt_simt(A, lda, B, ldb, M, N, K, epi, st);
+}
+
+__global__ void laplacian_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, const float *__restrict__ R,
+                                 int64_t ldr, int64_t r, int64_t f, float gamma, float *__restrict__ C0, int64_t ldc)
+{
+    // one warp per output element block: thread (i, j) loops over features; small shapes only
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= r || i >= n) return;
+    const float *x = X + i * ldx, *y = R + j * ldr;
+    float acc = 0.0f;
+    for (int64_t q = 0; q < f; ++q) acc += fabsf(__ldg(x + q) - __ldg(y + q));
+    C0[i * ldc + j] = expf(-gamma * acc);
+}
+
+}  // namespace gnngp
+
+using namespace gnngp;
+
+extern "C" {
+
+size_t gnngp_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 256;
+    return tc::workspace_bytes(M, N, K);
+}
+
+int gnngp_gemm_nt_f32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc, int64_t M,
+                      int64_t N, int64_t K, float alpha, float beta, void *workspace, size_t workspace_bytes,
+                      gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm_nt: negative size");
+    GNNGP_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm_nt: leading dimension too small");
+    GNNGP_REQUIRE(M == 0 || N == 0 || (A && B && C), "gemm_nt: null pointer");
+    EpiPlain epi{C, ldc, alpha, beta, aligned(C, 16) && ldc % 4 == 0};
+    return contract(A, lda, B, ldb, M, N, K, epi, workspace, workspace_bytes, as_stream(stream));
+}
+
+int gnngp_gram_arccos_f32(const float *Q, int64_t ldq, int64_t n, const float *L, int64_t ldl, int64_t n_land,
+                          int64_t m, const float *s, const float *t, float *E, int64_t lde, void *workspace,
+                          size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(n >= 0 && n_land >= 0 && m > 0, "gram_arccos: bad sizes");
+    GNNGP_REQUIRE(ldq >= m && ldl >= m && lde >= n_land, "gram_arccos: leading dimension too small");
+    GNNGP_REQUIRE(n == 0 || n_land == 0 || (Q && L && s && t && E), "gram_arccos: null pointer");
+    EpiArccos epi{s, t, E, lde, aligned(E, 16) && lde % 4 == 0 && aligned(t, 16)};
+    return contract(Q, ldq, L, ldl, n, n_land, m, epi, workspace, workspace_bytes, as_stream(stream));
+}
+
+int gnngp_initial_kernel_f32(int kind, const float *X, int64_t ldx, int64_t n, const float *R, int64_t ldr, int64_t r,
+                             int64_t f, const float *xx, const float *rr, float gamma, float c, float d, float *C0,
+                             int64_t ldc, void *workspace, size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(kind >= 0 && kind <= 4, "initial_kernel: unknown kind %d", kind);
+    GNNGP_REQUIRE(n >= 0 && r >= 0 && f > 0 && ldx >= f && ldr >= f && ldc >= r, "initial_kernel: bad sizes");
+    GNNGP_REQUIRE(kind != 1 || (xx && rr), "initial_kernel: rbf needs the squared row norms");
+    if (kind == 0) {
+        EpiPlain epi{C0, ldc, 1.0f, 0.0f, aligned(C0, 16) && ldc % 4 == 0};
+        return contract(X, ldx, R, ldr, n, r, f, epi, workspace, workspace_bytes, as_stream(stream));
+    }
+    EpiInitial epi{kind, xx, rr, gamma, c, d, C0, ldc};
+    return contract(X, ldx, R, ldr, n, r, f, epi, workspace, workspace_bytes, as_stream(stream));
+}
+
+int gnngp_laplacian_kernel_f32(const float *X, int64_t ldx, int64_t n, const float *R, int64_t ldr, int64_t r, int64_t f,
+                               float gamma, float *C0, int64_t ldc, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(n >= 0 && r >= 0 && f > 0 && ldx >= f && ldr >= f && ldc >= r, "laplacian_kernel: bad sizes");
+    GNNGP_REQUIRE(n <= 65535, "laplacian_kernel: n = %lld exceeds the grid limit of this small-shape kernel", (long long)n);
+    if (n == 0 || r == 0) return GNNGP_OK;
+    laplacian_kernel<<<dim3((unsigned)ceil_div(r, 128), (unsigned)n), 128, 0, as_stream(stream)>>>(X, ldx, n, R, ldr, r, f, gamma, C0, ldc);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+
+int gnngp_nugget_sweep_f32(const float *Q, int64_t ldq, int64_t n, int64_t m, const float *Bt, int64_t ldb, int64_t G,
+                           int64_t C, float *fitted, void *workspace, size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(n >= 0 && m > 0 && G > 0 && C > 0 && ldq >= m && ldb >= m, "nugget_sweep: bad sizes");
+    GNNGP_REQUIRE(G * C < ((int64_t)1 << 31), "nugget_sweep: G*C too large");
+    GNNGP_REQUIRE(n == 0 || (Q && Bt && fitted), "nugget_sweep: null pointer");
+    EpiSweep epi{fitted, n, C};
+    return contract(Q, ldq, Bt, ldb, n, G * C, m, epi, workspace, workspace_bytes, as_stream(stream));
+}
+
+}  // extern "C"

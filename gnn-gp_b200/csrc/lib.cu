@@ -1,0 +1,67 @@
+// Library-level entry points: error text, device info, engine switch, launch counter.
+#include <stdarg.h>
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gnngp {
+
+static thread_local char g_error[512] = "";
+static std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_gemm_engine{2};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace gnngp
+
+extern "C" {
+
+int gnngp_abi_version(void) { return 1; }
+
+const char *gnngp_last_error(void) { return gnngp::g_error; }
+
+int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor)
+{
+    int dev = 0;
+    GNNGP_CUDA(cudaGetDevice(&dev));
+    int sms = 0, major = 0, minor = 0;
+    GNNGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GNNGP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    GNNGP_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (host_sm_count) *host_sm_count = sms;
+    if (host_cc_major) *host_cc_major = major;
+    if (host_cc_minor) *host_cc_minor = minor;
+    return GNNGP_OK;
+}
+
+int gnngp_set_gemm_engine(int engine)
+{
+    if (engine < 0 || engine > 2) engine = 2;
+    return gnngp::g_gemm_engine.exchange(engine);
+}
+
+int64_t gnngp_launch_count(void) { return gnngp::g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+"""``GNNGP`` model class — drop-in for the reference's ``src/gnngp.py`` (same constructor, attributes
+and methods; ``src/gnngp.py:63-135``), computing on B200 through :mod:`gnngp_b200.compute` and
+:mod:`gnngp_b200.predict`."""
+from __future__ import annotations
+
+from typing import Union
+
+import torch
+from torch import Tensor
+
+from . import compute, datasets, predict
+
+
+class GNNGP(object):
+    """Infinite-width graph neural network Gaussian process.
+
+    Args / attributes: identical to the reference's ``GNNGP`` (``src/gnngp.py:6-62``):
+    ``data`` is a PyG-``Data``-like object (``x, y, edge_index, edge_attr, train_mask, val_mask,
+    test_mask`` and ``.to(device)``), ``method`` in {GCN, GCN2, GIN, SAGE, GGP, RBF}, ``initial`` in
+    {linear, rbf, laplacian, arccos, sigmoid, polynomial}; ``mask["landmark"]`` is set by the caller
+    for the Nystrom path.  The device must be a CUDA device: there is no CPU fallback.
+    """
+
+    _HYPER = ("L", "sigma_b", "sigma_w", "Nystrom", "initial", "method")
+
+    def __init__(self, data, device: torch.device = None, L: int = 2, sigma_b: float = 0.1, sigma_w: float = 1.0,
+                 Nystrom: bool = False, initial: str = "linear", method: str = "GCN", **params):
+        self.device = device
+        self.set_hyper_param(L, sigma_b, sigma_w, Nystrom, initial, method, **params)
+        graph = data.to(device)
+        self.N, self.X, self.y, self.A, self.mask = datasets.get_data(graph)
+
+    def set_hyper_param(self, L: int = None, sigma_b: float = None, sigma_w: float = None, Nystrom: bool = None,
+                        initial: str = None, method: str = None, **params) -> None:
+        """Update the hyper-parameters that are given, REPLACE the extra ``params`` and drop the cached
+        kernel — the contract of reference ``src/gnngp.py:71-85``."""
+        given = dict(zip(self._HYPER, (L, sigma_b, sigma_w, Nystrom, initial, method)))
+        for name, value in given.items():
+            if value is not None:
+                setattr(self, name, value)
+        self.params = params
+        self.computed = False
+
+    def _compute_kernel(self) -> None:
+        p = self.params
+        if self.Nystrom:
+            land = self.mask["landmark"]
+            self.Q0 = compute._init_kernel_Nystrom(self.X, land, self.initial, **p)
+            self.Q = compute._get_kernel_Nystrom(self.Q0, self.A, self.L, self.sigma_b, self.sigma_w, land,
+                                                 self.method, **p)
+        else:
+            self.C0 = compute._init_kernel(self.X, self.initial, **p)
+            self.K = compute._get_kernel(self.C0, self.A, self.L, self.sigma_b, self.sigma_w, self.method, **p)
+        self.computed = True
+
+    def get_kernel(self) -> Tensor:
+        """``Q`` (Nystrom) or ``K`` (exact); memoised until the next ``set_hyper_param``
+        (reference ``src/gnngp.py:87-99``)."""
+        if not self.computed:
+            self._compute_kernel()
+        return self.Q if self.Nystrom else self.K
+
+    def predict(self, nugget: Union[float, Tensor] = 1e-2):
+        """Posterior means for every nugget, then the per-mask metrics (reference ``src/gnngp.py:101-124``).
+        Sets ``fit``, ``result`` and ``nugget``; returns ``fit``.  For a single nugget the reference's
+        ``result`` mis-reads the squeezed ``fit``; here the metric is still computed per
+        nugget."""
+        kernel = self.get_kernel()
+        grid = torch.tensor([nugget]) if isinstance(nugget, float) else nugget
+        fit_fn = predict.fit_Nystrom if self.Nystrom else predict.fit
+        self.fit = fit_fn(kernel, self.y, self.mask["train"], grid)
+        per_nugget = self.fit if len(grid) > 1 else self.fit.unsqueeze(0)
+        self.result = predict.result(per_nugget, self.y, self.mask)
+        self.nugget = grid
+        return self.fit
+
+    def get_summary(self):
+        """Hyper-parameters plus, once ``predict`` has run, the nugget with the best validation metric and
+        the train / val / test metrics there (reference ``src/gnngp.py:126-135``)."""
+        summary = {name: getattr(self, name) for name in self._HYPER}
+        scores = getattr(self, "result", None)
+        if scores is not None:
+            best = torch.argmax(scores["val"])
+            summary["nugget"] = self.nugget[best]
+            for split in ("train", "val", "test"):
+                summary[split] = scores[split][best]
+        return summary

@@ -1,0 +1,395 @@
+"""Tensor-level operator set of the GNNGP hot path on B200.
+
+Every method enqueues hand-written sm_100a kernels of ``libgnngp_b200.so`` (through the C ABI of
+``include/gnngp_b200.h``) on torch's current CUDA stream.  PyTorch only owns memory, streams and the
+symmetric eigensolver call (``torch.linalg.eigh`` → cuSOLVER; SURVEY.md §7 hard part 1).  Inputs must
+be CUDA fp32 tensors; anything else raises — there is no CPU path.
+
+Matrices produced here are views ``buf[:, :m]`` of buffers whose leading dimension is padded to a
+multiple of 4 floats, so that the SpMM can gather them with 128-bit loads.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class CsrMatrix(object):
+    """Device CSR of the normalised adjacency (row pointer int64, column ids int32, values fp32).
+    ``row_offset`` / ``n_rows`` describe the row block a rank owns when the graph is row-sharded."""
+
+    def __init__(self, rowptr, colidx, vals, n_rows, n_cols, row_offset=0):
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.n_rows, self.n_cols, self.row_offset = int(n_rows), int(n_cols), int(row_offset)
+        self.nnz = int(colidx.numel())
+
+
+class CudaOps(object):
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        self.lib = _lib.library()
+        self._workspace = {}
+        self._csr_cache = {}
+        self.spmm_tile_cols = 0       # 0 = automatic (see gnngp_spmm_csr_f32)
+        self.spmm_nnz_per_warp = 0
+
+    # ------------------------------------------------------------------ plumbing
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _check(t: torch.Tensor, name: str, dtype=torch.float32, dims: Optional[int] = None) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError("gnngp_b200: %s must be a CUDA tensor (the hot path has no CPU fallback)" % name)
+        if t.dtype != dtype:
+            raise RuntimeError("gnngp_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+        if dims is not None and t.dim() != dims:
+            raise RuntimeError("gnngp_b200: %s must be %d-D" % (name, dims))
+        return t
+
+    def _mat(self, t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+        """Row-major matrix with unit column stride → (tensor, leading dimension)."""
+        self._check(t, name, dims=2)
+        if t.shape[1] > 1 and t.stride(1) != 1:
+            t = t.contiguous()
+        if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+            t = t.contiguous()
+        return t, self._ld(t)
+
+    @staticmethod
+    def _ld(t: torch.Tensor) -> int:
+        """Leading dimension of a row-major 2-D view (a single row may use any ld >= its width)."""
+        return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.shape[1]), 1)
+
+    def _vec(self, t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+        self._check(t, name, dtype=dtype, dims=1)
+        return t if t.numel() <= 1 or t.stride(0) == 1 else t.contiguous()
+
+    def workspace(self, nbytes: int, device, slot: str = "main") -> torch.Tensor:
+        key = (device.index, slot)
+        buf = self._workspace.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self._workspace[key] = None
+            buf = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
+            self._workspace[key] = buf
+        return buf
+
+    def release_workspace(self):
+        self._workspace.clear()
+
+    def empty(self, n: int, m: int, device) -> torch.Tensor:
+        buf = torch.empty((n, _round_up(max(m, 1), 4)), dtype=torch.float32, device=device)
+        return buf[:, :m]
+
+    def zeros(self, n: int, m: int, device) -> torch.Tensor:
+        buf = torch.zeros((n, _round_up(max(m, 1), 4)), dtype=torch.float32, device=device)
+        return buf[:, :m]
+
+    def launch_count(self) -> int:
+        return int(self.lib.query("gnngp_launch_count"))
+
+    def set_gemm_engine(self, engine: int) -> int:
+        return int(self.lib.query("gnngp_set_gemm_engine", int(engine)))
+
+    # ------------------------------------------------------------------ adjacency
+    def csr_from_coo(self, row: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n_rows: int, n_cols: int,
+                     row_offset: int = 0) -> CsrMatrix:
+        self._check(row, "row", torch.int64, 1)
+        self._check(col, "col", torch.int64, 1)
+        self._check(val, "val", torch.float32, 1)
+        row, col, val = row.contiguous(), col.contiguous(), val.contiguous()
+        nnz = row.numel()
+        dev = row.device
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+        vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz]
+        need = self.lib.query("gnngp_csr_from_coo_workspace_bytes", nnz, n_rows)
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)     # one-off, not kept
+        wptr = (ws.data_ptr() + 255) // 256 * 256
+        self.lib.call("gnngp_csr_from_coo", row.data_ptr(), col.data_ptr(), val.data_ptr(), nnz, n_rows, n_cols,
+                      rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), wptr, need, self._stream())
+        ws.record_stream(torch.cuda.current_stream())
+        return CsrMatrix(rowptr, colidx, vals, n_rows, n_cols, row_offset)
+
+    def csr_of(self, A: torch.Tensor) -> CsrMatrix:
+        """CSR of a torch sparse COO adjacency, converted once and cached on the tensor's storage."""
+        if isinstance(A, CsrMatrix):
+            return A
+        if not A.is_sparse:
+            raise RuntimeError("gnngp_b200: adjacency must be a torch sparse COO tensor")
+        idx, val = A._indices(), A._values()
+        key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index)
+        hit = self._csr_cache.get(key)
+        if hit is None:
+            if val.dtype != torch.float32:
+                val = val.to(torch.float32)
+            hit = self.csr_from_coo(idx[0], idx[1], val, A.shape[0], A.shape[1])
+            if len(self._csr_cache) > 8:
+                self._csr_cache.clear()
+            self._csr_cache[key] = hit
+        return hit
+
+    # ------------------------------------------------------------------ K1 SpMM
+    def spmm(self, csr: CsrMatrix, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, ldb = self._mat(B, "B")
+        if B.shape[0] != csr.n_cols:
+            raise RuntimeError("spmm: B has %d rows, adjacency has %d columns" % (B.shape[0], csr.n_cols))
+        k = B.shape[1]
+        if out is None:
+            out = self.empty(csr.n_rows, k, B.device)
+        self._check(out, "out", dims=2)
+        if out.shape != (csr.n_rows, k) or (k > 1 and out.stride(1) != 1):
+            raise RuntimeError("spmm: out must be a [%d x %d] row-major view" % (csr.n_rows, k))
+        self.lib.call("gnngp_spmm_csr_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(),
+                      csr.n_rows, csr.n_cols, csr.nnz, B.data_ptr(), ldb, k, float(alpha), out.data_ptr(),
+                      self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), self._stream())
+        return out
+
+    # ------------------------------------------------------------------ dense contractions
+    def _gemm_ws(self, M: int, N: int, K: int, device):
+        need = self.lib.query("gnngp_gemm_workspace_bytes", M, N, K)
+        ws = self.workspace(need + 256, device, "gemm")
+        return (ws.data_ptr() + 255) // 256 * 256, need
+
+    def gemm_nt(self, A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
+                beta: float = 0.0) -> torch.Tensor:
+        """out = alpha * A @ B.T (+ beta * out)."""
+        A, lda = self._mat(A, "A")
+        B, ldb = self._mat(B, "B")
+        M, K = A.shape
+        N = B.shape[0]
+        if B.shape[1] != K:
+            raise RuntimeError("gemm_nt: inner dimensions differ (%d vs %d)" % (K, B.shape[1]))
+        if out is None:
+            out = self.empty(M, N, A.device)
+        self._check(out, "out", dims=2)
+        if out.shape != (M, N) or (N > 1 and out.stride(1) != 1):
+            raise RuntimeError("gemm_nt: out must be a [%d x %d] row-major view" % (M, N))
+        ws, nbytes = self._gemm_ws(M, N, K, A.device)
+        self.lib.call("gnngp_gemm_nt_f32", A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), self._ld(out),
+                      M, N, K, float(alpha), float(beta), ws, nbytes, self._stream())
+        return out
+
+    def gram_arccos(self, Q: torch.Tensor, L: torch.Tensor, s: torch.Tensor, t: torch.Tensor,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """E = J1-arccos((Q L^T) / s / t^T) * s * t^T — reference ``_ExxT_ReLU_Nystrom`` before the root."""
+        Q, ldq = self._mat(Q, "Q")
+        L, ldl = self._mat(L, "L")
+        s, t = self._vec(s, "s"), self._vec(t, "t")
+        n, m = Q.shape
+        nl = L.shape[0]
+        if L.shape[1] != m or s.numel() != n or t.numel() != nl:
+            raise RuntimeError("gram_arccos: shape mismatch")
+        if out is None:
+            out = self.empty(n, nl, Q.device)
+        ws, nbytes = self._gemm_ws(n, nl, m, Q.device)
+        self.lib.call("gnngp_gram_arccos_f32", Q.data_ptr(), ldq, n, L.data_ptr(), ldl, nl, m, s.data_ptr(), t.data_ptr(),
+                      out.data_ptr(), self._ld(out), ws, nbytes, self._stream())
+        return out
+
+    KINDS = {"linear": 0, "rbf": 1, "sigmoid": 2, "polynomial": 3, "arccos": 4}
+
+    def initial_kernel(self, kind: str, X: torch.Tensor, R: torch.Tensor, gamma: float = 0.0, c: float = 0.0,
+                       d: float = 1.0) -> torch.Tensor:
+        X, ldx = self._mat(X, "X")
+        R, ldr = self._mat(R, "R")
+        n, f = X.shape
+        r = R.shape[0]
+        out = self.empty(n, r, X.device)
+        ldo = self._ld(out)
+        if kind == "laplacian":
+            self.lib.call("gnngp_laplacian_kernel_f32", X.data_ptr(), ldx, n, R.data_ptr(), ldr, r, f, float(gamma),
+                          out.data_ptr(), ldo, self._stream())
+            return out
+        xx = rr = None
+        if kind == "rbf":
+            xx = self.row_norms(X, sqrt=False)
+            rr = self.row_norms(R, sqrt=False)
+        ws, nbytes = self._gemm_ws(n, r, f, X.device)
+        self.lib.call("gnngp_initial_kernel_f32", self.KINDS[kind], X.data_ptr(), ldx, n, R.data_ptr(), ldr, r, f,
+                      xx.data_ptr() if xx is not None else None, rr.data_ptr() if rr is not None else None,
+                      float(gamma), float(c), float(d), out.data_ptr(), ldo, ws, nbytes, self._stream())
+        return out
+
+    def nugget_coeff(self, temp: torch.Tensor, w: torch.Tensor, eps: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+        temp, ldt = self._mat(temp, "temp")
+        w, eps = self._vec(w, "w"), self._vec(eps, "eps")
+        self._check(d, "d")
+        m, C = temp.shape
+        G = eps.numel()
+        S = self.empty(G * C, m, temp.device)
+        self.lib.call("gnngp_nugget_coeff_f32", temp.data_ptr(), ldt, w.data_ptr(), eps.data_ptr(), d.data_ptr(), m, C, G,
+                      S.data_ptr(), self._ld(S), self._stream())
+        return S
+
+    def nugget_sweep(self, Q: torch.Tensor, Bt: torch.Tensor, G: int, C: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        Q, ldq = self._mat(Q, "Q")
+        Bt, ldb = self._mat(Bt, "Bt")
+        n, m = Q.shape
+        if Bt.shape != (G * C, m):
+            raise RuntimeError("nugget_sweep: Bt must be [%d x %d]" % (G * C, m))
+        if out is None:
+            out = torch.empty((G, n, C), dtype=torch.float32, device=Q.device)
+        ws, nbytes = self._gemm_ws(n, G * C, m, Q.device)
+        self.lib.call("gnngp_nugget_sweep_f32", Q.data_ptr(), ldq, n, m, Bt.data_ptr(), ldb, G, C, out.data_ptr(), ws, nbytes,
+                      self._stream())
+        return out
+
+    # ------------------------------------------------------------------ rows / columns
+    def row_norms(self, Q: torch.Tensor, sqrt: bool = True) -> torch.Tensor:
+        Q, ldq = self._mat(Q, "Q")
+        out = torch.empty(_round_up(max(Q.shape[0], 1), 4), dtype=torch.float32, device=Q.device)[:Q.shape[0]]
+        self.lib.call("gnngp_row_sumsq_f32", Q.data_ptr(), ldq, Q.shape[0], Q.shape[1], 1 if sqrt else 0, out.data_ptr(),
+                      self._stream())
+        return out
+
+    def mean(self, v: torch.Tensor, stride: int = 1, count: Optional[int] = None) -> torch.Tensor:
+        self._check(v, "v")
+        n = int(v.numel() if count is None else count)
+        out = torch.empty(1, dtype=torch.float32, device=v.device)
+        self.lib.call("gnngp_mean_f32", v.data_ptr(), n, int(stride), out.data_ptr(), self._stream())
+        return out
+
+    def diag_mean(self, K: torch.Tensor) -> torch.Tensor:
+        K, ldk = self._mat(K, "K")
+        return self.mean(K, stride=ldk + 1, count=K.shape[0])
+
+    def fill_col(self, M: torch.Tensor, col: int, value: float) -> None:
+        self._check(M, "M", dims=2)
+        view = M[:, col]
+        self.lib.call("gnngp_fill_col_f32", view.data_ptr(), self._ld(M), M.shape[0], float(value), self._stream())
+
+    def gather_rows(self, src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        src, lds = self._mat(src, "src")
+        idx = self._vec(idx, "idx", torch.int64)
+        out = self.empty(idx.numel(), src.shape[1], src.device)
+        self.lib.call("gnngp_gather_rows_f32", src.data_ptr(), lds, idx.data_ptr(), idx.numel(), src.shape[1],
+                      out.data_ptr(), self._ld(out), self._stream())
+        return out
+
+    def scatter_rows(self, dst: torch.Tensor, idx: torch.Tensor, src: torch.Tensor) -> None:
+        src, lds = self._mat(src, "src")
+        self._check(dst, "dst", dims=2)
+        idx = self._vec(idx, "idx", torch.int64)
+        if dst.shape[1] != src.shape[1] or (dst.shape[1] > 1 and dst.stride(1) != 1):
+            raise RuntimeError("scatter_rows: column mismatch")
+        self.lib.call("gnngp_scatter_rows_f32", src.data_ptr(), lds, idx.data_ptr(), idx.numel(), src.shape[1],
+                      dst.data_ptr(), self._ld(dst), self._stream())
+
+    def gather_rows_t(self, src: torch.Tensor, idx: Optional[torch.Tensor]) -> torch.Tensor:
+        """out[c, r] = src[idx[r], c]; ``idx=None`` is a plain transpose."""
+        src, lds = self._mat(src, "src")
+        n_idx = src.shape[0] if idx is None else idx.numel()
+        if idx is not None:
+            idx = self._vec(idx, "idx", torch.int64)
+        out = self.empty(src.shape[1], n_idx, src.device)
+        self.lib.call("gnngp_gather_rows_transposed_f32", src.data_ptr(), lds, idx.data_ptr() if idx is not None else None,
+                      n_idx, src.shape[1], out.data_ptr(), self._ld(out),
+                      self._stream())
+        return out
+
+    def transpose(self, src: torch.Tensor) -> torch.Tensor:
+        return self.gather_rows_t(src, None)
+
+    def gather_cols(self, src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        src, lds = self._mat(src, "src")
+        idx = self._vec(idx, "idx", torch.int64)
+        out = self.empty(src.shape[0], idx.numel(), src.device)
+        self.lib.call("gnngp_gather_cols_f32", src.data_ptr(), lds, src.shape[0], idx.data_ptr(), idx.numel(), out.data_ptr(),
+                      self._ld(out), self._stream())
+        return out
+
+    def affine(self, out: torch.Tensor, x: torch.Tensor, y: Optional[torch.Tensor], a: float, b: float, c: float) -> torch.Tensor:
+        """out = a*x + b*y + c (elementwise, in place allowed)."""
+        for name, t in (("out", out), ("x", x)) + ((("y", y),) if y is not None else ()):
+            self._check(t, name, dims=2)
+            if t.shape != out.shape or (t.shape[1] > 1 and t.stride(1) != 1):
+                raise RuntimeError("affine: %s must be a row-major view of the output shape" % name)
+        n, m = out.shape
+        self.lib.call("gnngp_affine_f32", out.data_ptr(), self._ld(out), x.data_ptr(), self._ld(x),
+                      y.data_ptr() if y is not None else None, self._ld(y) if y is not None else 0, n, m,
+                      float(a), float(b), float(c), self._stream())
+        return out
+
+    # ------------------------------------------------------------------ Nystrom root pieces
+    def eigh(self, M: torch.Tensor):
+        """Symmetric eigendecomposition (ascending), cuSOLVER through torch — the one library call kept."""
+        self._check(M, "M", dims=2)
+        return torch.linalg.eigh(M if M.is_contiguous() else M.contiguous())
+
+    def nystrom_spectrum(self, D: torch.Tensor):
+        D = self._vec(D, "D")
+        root = torch.empty_like(D)
+        inv = torch.empty_like(D)
+        self.lib.call("gnngp_nystrom_spectrum_f32", D.data_ptr(), D.numel(), root.data_ptr(), inv.data_ptr(), self._stream())
+        return root, inv
+
+    def scale_cols(self, V: torch.Tensor, d: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        V, ldv = self._mat(V, "V")
+        d = self._vec(d, "d")
+        n, m = V.shape
+        out = self.empty(m, n, V.device) if transpose else self.empty(n, m, V.device)
+        self.lib.call("gnngp_scale_cols_f32", V.data_ptr(), ldv, n, m, d.data_ptr(), 1 if transpose else 0, out.data_ptr(),
+                      self._ld(out), self._stream())
+        return out
+
+    def arccos_dense(self, K: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        K, ldk = self._mat(K, "K")
+        n = K.shape[0]
+        if out is None:
+            out = self.empty(n, n, K.device)
+        s = torch.empty(n, dtype=torch.float32, device=K.device)
+        self.lib.call("gnngp_arccos_dense_f32", K.data_ptr(), ldk, n, out.data_ptr(), self._ld(out),
+                      s.data_ptr(), self._stream())
+        return out
+
+    # ------------------------------------------------------------------ targets / metrics
+    def onehot_t(self, y: torch.Tensor, idx: torch.Tensor, C: int) -> torch.Tensor:
+        y = self._vec(y, "y", torch.int64)
+        idx = self._vec(idx, "idx", torch.int64)
+        out = self.empty(C, idx.numel(), y.device)
+        self.lib.call("gnngp_onehot_t_f32", y.data_ptr(), idx.data_ptr(), idx.numel(), C, out.data_ptr(),
+                      self._ld(out), self._stream())
+        return out
+
+    def argmax_count(self, fitted: torch.Tensor, y: torch.Tensor, membership: torch.Tensor) -> torch.Tensor:
+        self._check(fitted, "fitted", dims=3)
+        fitted = fitted.contiguous()
+        y = self._vec(y, "y", torch.int64)
+        self._check(membership, "membership", torch.uint8, 1)
+        G, n, C = fitted.shape
+        counts = torch.empty((G, 8), dtype=torch.int32, device=fitted.device)
+        self.lib.call("gnngp_argmax_count", fitted.data_ptr(), y.data_ptr(), membership.data_ptr(), G, n, C, counts.data_ptr(),
+                      self._stream())
+        return counts
+
+    def sqerr_sum(self, fitted: torch.Tensor, y: torch.Tensor, membership: torch.Tensor) -> torch.Tensor:
+        self._check(fitted, "fitted")
+        fitted = fitted.contiguous()
+        y = self._check(y, "y").contiguous()
+        G, n = fitted.shape[0], fitted.shape[1]
+        k = int(fitted[0, 0].numel())
+        sse = torch.empty((G, 8), dtype=torch.float64, device=fitted.device)
+        self.lib.call("gnngp_sqerr_sum", fitted.data_ptr(), y.data_ptr(), membership.data_ptr(), G, n, k, sse.data_ptr(),
+                      self._stream())
+        return sse
+
+
+_OPS = None
+
+
+def default_ops() -> CudaOps:
+    """The process-wide operator set.  Raises if the CUDA library is not built."""
+    global _OPS
+    if _OPS is None:
+        _OPS = CudaOps()
+    return _OPS

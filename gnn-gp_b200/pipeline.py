@@ -1,0 +1,390 @@
+"""Host-side assembly of the GNNGP kernel recursion and GP inference out of the CUDA operator set.
+
+One code path serves a single GPU and the row-sharded multi-GPU mode: every matrix
+here is the block of node rows the calling rank owns, and the three places where the algorithm needs
+other ranks' rows go through a ``comm`` object — all-gather of the factor being propagated (before
+each SpMM), all-reduce of the landmark rows / landmark Gram block, all-reduce of ``Q_bᵀQ_b`` and
+``Q_bᵀy_b`` in the fit.  With ``LocalComm`` (world size 1) those are no-ops.
+
+Reference lines followed: ``src/compute.py:6-17`` (Nystrom root), ``41-67`` (initial factor),
+``120-127`` (ReLU expectation on the factor), ``139-146/160-171/183-190/202-210`` (layer loops),
+``110-117/130-136/149-157/174-180/193-199`` (exact path), ``src/predict.py:6-90`` (fit, result).
+Because every consumer of ``Q`` only uses ``Q Qᵀ``-invariant quantities, results are compared through
+``Q Qᵀ``, posterior means and predictions — never ``Q`` itself (eigenvector sign / rotation freedom).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+
+class LocalComm(object):
+    """World of one: the single-GPU drop-in path."""
+    world = 1
+    rank = 0
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    def all_gather_rows(self, block: torch.Tensor, layout: "RowLayout") -> torch.Tensor:
+        return block
+
+
+class RowLayout(object):
+    """Contiguous, equal-sized row blocks: rank r owns rows [r*rows_per_rank, min(N, (r+1)*rows_per_rank))."""
+
+    def __init__(self, n: int, world: int = 1, rank: int = 0):
+        self.n, self.world, self.rank = int(n), int(world), int(rank)
+        self.rows_per_rank = (self.n + self.world - 1) // self.world
+        self.begin = min(self.n, self.rank * self.rows_per_rank)
+        self.end = min(self.n, self.begin + self.rows_per_rank)
+        self.n_local = self.end - self.begin
+
+    def local_index(self, global_mask: torch.Tensor):
+        """(local row ids of the mask's members in this block, their positions in the global member order)."""
+        gidx = torch.nonzero(global_mask, as_tuple=False).flatten()
+        inside = (gidx >= self.begin) & (gidx < self.end)
+        pos = torch.nonzero(inside, as_tuple=False).flatten()
+        return (gidx[pos] - self.begin).contiguous(), pos.contiguous(), int(gidx.numel())
+
+
+class Landmarks(object):
+    def __init__(self, mask: torch.Tensor, layout: RowLayout):
+        self.local_rows, self.local_pos, self.count = layout.local_index(mask)
+
+
+def _row_block(na_ld: int, n_local: int) -> int:
+    """Rows per streamed block of the fused Gram → arc-cosine → back-projection (≤ ~1 GiB of E)."""
+    rows = max(1024, (1 << 28) // max(na_ld, 1))
+    rows = max(128, rows // 128 * 128)
+    return min(rows, max(n_local, 1))
+
+
+class Pipeline(object):
+    def __init__(self, ops, comm=None, layout: Optional[RowLayout] = None):
+        self.ops = ops
+        self.comm = comm if comm is not None else LocalComm()
+        self.layout = layout
+
+    def _layout(self, n_local: int) -> RowLayout:
+        if self.layout is None:
+            return RowLayout(n_local, 1, 0)
+        return self.layout
+
+    # ------------------------------------------------------------------ shared pieces
+    def landmark_rows(self, block: torch.Tensor, land: Landmarks) -> torch.Tensor:
+        """Rows of the landmark nodes, in global landmark order, replicated on every rank."""
+        ops = self.ops
+        mine = ops.gather_rows(block, land.local_rows)
+        if self.comm.world == 1:
+            return mine
+        full = ops.zeros(land.count, block.shape[1], block.device)
+        ops.scatter_rows(full, land.local_pos, mine)
+        self.comm.all_reduce_sum(full)
+        return full
+
+    def _root_factors(self, kmm: torch.Tensor):
+        """eigh of the landmark block and the two column scalings of src/compute.py:11-13."""
+        ops = self.ops
+        evals, evecs = ops.eigh(kmm)
+        root, inv = ops.nystrom_spectrum(evals)
+        w_t = ops.scale_cols(evecs, inv, transpose=True)      # (V * D^-1/2~)^T, the B operand of E @ (V D~)
+        v_root = ops.scale_cols(evecs, root)                   # V * sqrt(D+): the landmark rows of the factor
+        return w_t, v_root
+
+    def _put_landmark_rows(self, out: torch.Tensor, v_root: torch.Tensor, land: Landmarks) -> None:
+        ops = self.ops
+        rows = v_root if self.comm.world == 1 else ops.gather_rows(v_root, land.local_pos)
+        ops.scatter_rows(out, land.local_rows, rows)
+
+    def nystrom_root(self, k_cols: torch.Tensor, land: Landmarks) -> torch.Tensor:
+        """``_sqrt_Nystrom`` (src/compute.py:6-17) on this rank's rows of the landmark columns."""
+        ops = self.ops
+        kmm = self.landmark_rows(k_cols, land)
+        w_t, v_root = self._root_factors(kmm)
+        out = ops.gemm_nt(k_cols, w_t)
+        self._put_landmark_rows(out, v_root, land)
+        return out
+
+    def relu_nystrom(self, q: torch.Tensor, land: Landmarks) -> torch.Tensor:
+        """``_ExxT_ReLU_Nystrom`` (src/compute.py:120-127): landmark Gram with the arc-cosine expectation
+        fused into its epilogue, then the Nystrom root.  The N x N_a matrix E is never materialised:
+        row blocks are streamed Gram → J1 → back-projection."""
+        ops = self.ops
+        n_local, na = q.shape[0], land.count
+        s = ops.row_norms(q)
+        lrows = self.landmark_rows(q, land)
+        t = ops.row_norms(lrows)
+        emm = ops.gram_arccos(lrows, lrows, t, t)
+        w_t, v_root = self._root_factors(emm)
+        out = ops.empty(n_local, na, q.device)
+        rb = _row_block(w_t.stride(0), n_local)
+        scratch = ops.empty(rb, na, q.device)
+        for r0 in range(0, n_local, rb):
+            r1 = min(n_local, r0 + rb)
+            e_blk = ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=scratch[:r1 - r0])
+            ops.gemm_nt(e_blk, w_t, out=out[r0:r1])
+        self._put_landmark_rows(out, v_root, land)
+        return out
+
+    def propagate(self, csr, block: torch.Tensor, alpha: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``alpha * A @ X`` for this rank's rows of A: all-gather X's row blocks, then the CSR SpMM."""
+        full = self.comm.all_gather_rows(block, self._layout(block.shape[0]))
+        return self.ops.spmm(csr, full, alpha, out=out)
+
+    # ------------------------------------------------------------------ initial factor / kernel
+    def initial_columns(self, x: torch.Tensor, ref_rows: torch.Tensor, initial: str, params: dict) -> torch.Tensor:
+        ops = self.ops
+        if initial == "linear":
+            return ops.gemm_nt(x, ref_rows)
+        if initial == "rbf":
+            return ops.initial_kernel("rbf", x, ref_rows, gamma=float(params["gamma"]))
+        if initial == "laplacian":
+            return ops.initial_kernel("laplacian", x, ref_rows, gamma=float(params["gamma"]))
+        if initial == "sigmoid":
+            return ops.initial_kernel("sigmoid", x, ref_rows, gamma=float(params["gamma"]), c=float(params["c"]))
+        if initial == "polynomial":
+            return ops.initial_kernel("polynomial", x, ref_rows, c=float(params["c"]), d=float(params["d"]))
+        raise Exception("Unsupported kernel function!")
+
+    def initial_kernel(self, x: torch.Tensor, initial: str, params: dict) -> torch.Tensor:
+        """``C0`` — ``_init_kernel`` (src/compute.py:20-38); single rank only."""
+        if initial == "arccos":
+            # torch.corrcoef treats rows as variables: centre and normalise every row, then 1 - acos(.)/pi
+            z = x - x.mean(dim=1, keepdim=True)
+            z = z / torch.sqrt((z * z).sum(dim=1, keepdim=True))
+            return self.ops.initial_kernel("arccos", z, z)
+        return self.initial_columns(x, x, initial, params)
+
+    def initial_factor(self, x: torch.Tensor, land: Landmarks, initial: str, params: dict,
+                       column_stats=None) -> torch.Tensor:
+        """``Q0`` — ``_init_kernel_Nystrom`` (src/compute.py:41-67) for this rank's rows of X."""
+        if initial == "linear" and land.count >= x.shape[1]:
+            return x
+        feats = x
+        kind = initial
+        if initial == "arccos":
+            # column-centred, column-normalised features (src/compute.py:55-56); statistics are global
+            mean, norm = column_stats if column_stats is not None else self.column_stats(x)
+            feats = (x - mean) / norm
+        ref_rows = self.landmark_rows(feats, land)
+        if kind == "arccos":
+            cols = self.ops.initial_kernel("arccos", feats, ref_rows)
+        else:
+            cols = self.initial_columns(feats, ref_rows, kind, params)
+        return self.nystrom_root(cols, land)
+
+    def column_stats(self, x: torch.Tensor):
+        n_total = torch.tensor([float(x.shape[0])], device=x.device)
+        total = x.sum(dim=0, keepdim=True)
+        if self.comm.world > 1:
+            self.comm.all_reduce_sum(total)
+            self.comm.all_reduce_sum(n_total)
+        mean = total / n_total
+        sq = ((x - mean) ** 2).sum(dim=0, keepdim=True)
+        if self.comm.world > 1:
+            self.comm.all_reduce_sum(sq)
+        return mean, torch.sqrt(sq)
+
+    # ------------------------------------------------------------------ Nystrom layer recursions
+    def kernel_nystrom(self, q0: torch.Tensor, csr, layers: int, sigma_b: float, sigma_w: float, land: Landmarks,
+                       method: str, params: dict) -> torch.Tensor:
+        ops = self.ops
+        n, ni = q0.shape
+        na = land.count
+        dev = q0.device
+        if method == "GGP":
+            return self.propagate(csr, q0, 1.0)
+        if method == "RBF":
+            return q0
+        if method == "GCN":
+            q = ops.zeros(n, na + 1, dev)
+            self.propagate(csr, q0, sigma_w, out=q[:, :ni])
+            ops.fill_col(q, na, sigma_b)
+            for _ in range(layers - 1):
+                e = self.relu_nystrom(q, land)
+                self.propagate(csr, e, sigma_w, out=q[:, :na])
+                ops.fill_col(q, na, sigma_b)
+            return q
+        if method == "GIN":
+            q = ops.zeros(n, na + 1, dev)
+            self.propagate(csr, q0, sigma_w, out=q[:, :ni])
+            ops.fill_col(q, na, sigma_b)
+            for _ in range(layers - 1):
+                e = self.relu_nystrom(q, land)
+                ops.affine(q[:, :na], e, None, sigma_w, 0.0, 0.0)
+                ops.fill_col(q, na, sigma_b)
+            return q
+        if method == "SAGE":
+            q = ops.zeros(n, 2 * na, dev)
+            ops.affine(q[:, :ni], q0, None, sigma_b, 0.0, 0.0)
+            self.propagate(csr, q0, sigma_w, out=q[:, ni:2 * ni])
+            for _ in range(layers - 1):
+                e = self.relu_nystrom(q, land)
+                ops.affine(q[:, :na], e, None, sigma_b, 0.0, 0.0)
+                self.propagate(csr, e, sigma_w, out=q[:, na:])
+            return q
+        if method == "GCN2":
+            alpha = params.get("alpha", 0.1)
+            theta = params.get("theta", 0.5)
+            e = self.relu_nystrom(q0, land)
+            q = ops.zeros(n, na + ni, dev)
+            self.propagate(csr, e, sigma_w, out=q[:, :na])
+            for j in range(layers - 1):
+                e = self.relu_nystrom(q, land)
+                beta = math.log(theta / (j + 1) + 1)
+                coef = math.sqrt((sigma_w * beta) ** 2 + (1 - beta) ** 2)
+                self.propagate(csr, e, (1 - alpha) * coef, out=q[:, :na])
+                ops.affine(q[:, na:na + ni], q0, None, alpha * coef, 0.0, 0.0)
+            return q
+        raise Exception("Unsupported layer type!")
+
+    # ------------------------------------------------------------------ exact layer recursions (single rank)
+    def _sandwich(self, csr, dense: torch.Tensor, factor: float) -> torch.Tensor:
+        """``factor * A @ (A @ dense).T`` evaluated in the reference's order (src/compute.py:132)."""
+        ops = self.ops
+        inner = ops.spmm(csr, dense)
+        return ops.spmm(csr, ops.transpose(inner), factor)
+
+    def kernel_exact(self, c0: torch.Tensor, csr, layers: int, sigma_b: float, sigma_w: float, method: str,
+                     params: dict) -> torch.Tensor:
+        ops = self.ops
+        b2, w2 = sigma_b ** 2, sigma_w ** 2
+        if method == "GGP":
+            return self._sandwich(csr, c0, 1.0)
+        if method == "RBF":
+            return c0
+        if method == "GCN":
+            k = self._sandwich(csr, c0, w2)
+            ops.affine(k, k, None, 1.0, 0.0, b2)
+            for _ in range(layers - 1):
+                e = ops.arccos_dense(k)
+                k = self._sandwich(csr, e, w2)
+                ops.affine(k, k, None, 1.0, 0.0, b2)
+            return k
+        if method == "GIN":
+            k = self._sandwich(csr, c0, w2)
+            ops.affine(k, k, None, 1.0, 0.0, b2)
+            for _ in range(layers - 1):
+                e = ops.arccos_dense(k)
+                ops.affine(k, e, None, w2, 0.0, b2)
+            return k
+        if method == "SAGE":
+            k = self._sandwich(csr, c0, w2)
+            ops.affine(k, k, c0, 1.0, b2, 0.0)
+            for _ in range(layers - 1):
+                e = ops.arccos_dense(k)
+                k = self._sandwich(csr, e, w2)
+                ops.affine(k, k, e, 1.0, b2, 0.0)
+            return k
+        if method == "GCN2":
+            alpha = params.get("alpha", 0.1)
+            theta = params.get("theta", 0.5)
+            k = self._sandwich(csr, ops.arccos_dense(c0), w2)
+            for j in range(layers - 1):
+                e = ops.arccos_dense(k)
+                beta = math.log(theta / (j + 1) + 1)
+                coef = (sigma_w * beta) ** 2 + (1 - beta) ** 2
+                k = self._sandwich(csr, e, (1 - alpha) ** 2)
+                ops.affine(k, k, c0, coef, coef * alpha ** 2, 0.0)
+            return k
+        raise Exception("Unsupported layer type!")
+
+    # ------------------------------------------------------------------ GP inference
+    def _targets_t(self, y: torch.Tensor, rows: torch.Tensor, num_classes: Optional[int]):
+        """Transposed targets of the training rows: one-hot [C x n_t] for integer labels
+        (src/predict.py:23-24), the raw values [k x n_t] otherwise.  Returns (Yt, trailing shape)."""
+        ops = self.ops
+        if not y.dtype.is_floating_point:
+            return ops.onehot_t(y.to(torch.int64), rows, int(num_classes)), (int(num_classes),)
+        y2 = y.reshape(y.shape[0], -1).to(torch.float32)
+        return ops.gather_rows_t(y2, rows), tuple(y.shape[1:])
+
+    def _sweep(self, left: torch.Tensor, evals, evecs, proj_t: torch.Tensor, scale: torch.Tensor, nugget: torch.Tensor,
+               trailing) -> torch.Tensor:
+        """All nuggets at once (src/predict.py:31-32 / 61-62).  ``proj_t`` is (Vᵀ·targets)ᵀ, [C x m]."""
+        ops = self.ops
+        temp = ops.transpose(proj_t)                                  # [m x C]
+        coeff = ops.nugget_coeff(temp, evals, nugget, scale)          # [(G*C) x m]
+        b_t = ops.gemm_nt(coeff, evecs)                               # [(G*C) x m]: (V diag(1/(w+eps d)) temp)^T
+        g, c = nugget.numel(), temp.shape[1]
+        fitted = ops.nugget_sweep(left, b_t, g, c)                    # [G, n, C]
+        fitted = fitted.reshape((g, left.shape[0]) + tuple(trailing))
+        return fitted[0] if g == 1 else fitted
+
+    def fit_nystrom(self, q: torch.Tensor, y: torch.Tensor, train_rows: torch.Tensor, nugget: torch.Tensor,
+                    n_total: Optional[int] = None, num_classes: Optional[int] = None) -> torch.Tensor:
+        """``fit_Nystrom`` (src/predict.py:36-63) for this rank's rows."""
+        ops, comm = self.ops, self.comm
+        n_total = q.shape[0] if n_total is None else n_total
+        qb_t = ops.gather_rows_t(q, train_rows)                       # [m x n_t]
+        gram = ops.gemm_nt(qb_t, qb_t)                                # Q_b^T Q_b
+        y_t, trailing = self._targets_t(y, train_rows, num_classes)
+        qty_t = ops.gemm_nt(y_t, qb_t)                                # (Q_b^T y_b)^T  [C x m]
+        sumsq = ops.row_norms(q, sqrt=False)
+        scale = ops.mean(sumsq) * (float(q.shape[0]) / float(n_total)) if q.shape[0] > 0 else torch.zeros(1, device=q.device)
+        if comm.world > 1:
+            comm.all_reduce_sum(gram)
+            comm.all_reduce_sum(qty_t)
+            comm.all_reduce_sum(scale)
+        evals, evecs = ops.eigh(gram)
+        proj_t = ops.gemm_nt(qty_t, ops.transpose(evecs))             # (V^T Q_b^T y_b)^T  [C x m]
+        return self._sweep(q, evals, evecs, proj_t, scale, nugget, trailing)
+
+    def fit_exact(self, k: torch.Tensor, y: torch.Tensor, train_rows: torch.Tensor, nugget: torch.Tensor,
+                  num_classes: Optional[int] = None) -> torch.Tensor:
+        """``fit`` (src/predict.py:6-33); single rank only."""
+        ops = self.ops
+        k_cols = ops.gather_cols(k, train_rows)                       # K[:, mb]
+        k_bb = ops.gather_rows(k_cols, train_rows)                    # K[mb][:, mb]
+        evals, evecs = ops.eigh(k_bb)
+        scale = ops.diag_mean(k)
+        y_t, trailing = self._targets_t(y, train_rows, num_classes)   # [C x n_t]
+        proj_t = ops.gemm_nt(y_t, ops.transpose(evecs))               # (V^T y_b)^T
+        return self._sweep(k_cols, evals, evecs, proj_t, scale, nugget, trailing)
+
+    def metrics(self, fitted: torch.Tensor, y: torch.Tensor, masks: Dict[str, torch.Tensor],
+                totals: Optional[Dict[str, float]] = None) -> Dict[str, torch.Tensor]:
+        """``result`` (src/predict.py:66-90): accuracy for integer targets, R² for float targets, per
+        nugget and per mask; CPU fp32 tensors like the reference.  One fused pass per 8 masks."""
+        ops, comm = self.ops, self.comm
+        names = list(masks)
+        classify = not y.dtype.is_floating_point
+        g = fitted.shape[0]
+        out = {}
+        for base in range(0, len(names), 8):
+            group = names[base:base + 8]
+            member = torch.zeros(y.shape[0], dtype=torch.uint8, device=y.device)
+            for bit, name in enumerate(group):
+                member |= masks[name].to(torch.uint8) << bit
+            if classify:
+                stat = ops.argmax_count(fitted, y.to(torch.int64), member).to(torch.float64)
+                size = torch.stack([masks[name].sum() for name in group]).to(torch.float64)
+                pack = torch.cat([stat[:, :len(group)].reshape(-1), size])
+                if comm.world > 1:
+                    comm.all_reduce_sum(pack)
+                pack = pack.cpu()
+                stat, size = pack[:g * len(group)].reshape(g, len(group)), pack[g * len(group):]
+                for bit, name in enumerate(group):
+                    out[name] = (stat[:, bit].to(torch.float32) / size[bit].to(torch.float32))
+            else:
+                yf = y.to(torch.float32)
+                sse = ops.sqerr_sum(fitted, yf, member)
+                y2 = yf.reshape(yf.shape[0], -1).to(torch.float64)
+                sums = []
+                for name in group:
+                    sel = masks[name].to(torch.float64).unsqueeze(1)
+                    sums.append(torch.stack([sel.sum() * y2.shape[1], (sel * y2).sum(), (sel * y2 * y2).sum()]))
+                pack = torch.cat([sse[:, :len(group)].reshape(-1), torch.stack(sums).reshape(-1)])
+                if comm.world > 1:
+                    comm.all_reduce_sum(pack)
+                pack = pack.cpu()
+                sse_c = pack[:g * len(group)].reshape(g, len(group))
+                mom = pack[g * len(group):].reshape(len(group), 3)
+                for bit, name in enumerate(group):
+                    cnt, s1, s2 = mom[bit]
+                    sst = s2 - s1 * s1 / cnt                           # sum (y - mean y)^2 over the subset
+                    out[name] = (1.0 - sse_c[:, bit] / sst).to(torch.float32)
+        return out

@@ -1,0 +1,165 @@
+/*
+ * gnngp_b200.h — C ABI of the B200 (sm_100a) GNNGP hot path.
+ *
+ * The reference (niuzehao/gnn-gp) has no FFI: its hot path is Python calling ATen
+ * (cuSPARSE / cuBLAS / cuSOLVER / TensorIterator kernels).  Each entry point below replaces the
+ * ATen call(s) at the cited reference lines (paths relative to /root/reference); the Python
+ * surface that binds them (gnn-gp_b200/{compute,predict,gnngp}.py) keeps the reference's function
+ * names and signatures.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the library never allocates or frees
+ *     caller-visible device memory; scratch comes in through (workspace, workspace_bytes) where needed
+ *   - matrices are fp32 row-major with an explicit leading dimension (elements, not bytes)
+ *   - one call = kernels enqueued on `stream` (a cudaStream_t), no host synchronisation
+ *   - return 0 on success, a negative gnngp_status otherwise; gnngp_last_error() has the text
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with GNNGP_ERR_CUDA
+ */
+#ifndef GNNGP_B200_H_
+#define GNNGP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *gnngp_stream_t; /* cudaStream_t */
+
+enum gnngp_status {
+    GNNGP_OK = 0,
+    GNNGP_ERR_ARG = -1,       /* bad size / null pointer / misaligned buffer */
+    GNNGP_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+    GNNGP_ERR_WORKSPACE = -3, /* workspace too small */
+    GNNGP_ERR_UNSUPPORTED = -4
+};
+
+/* ---- library ---------------------------------------------------------------------------- */
+int gnngp_abi_version(void);
+const char *gnngp_last_error(void);
+/* SM count and compute capability of the current device (host out-pointers). */
+int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor);
+/* Dense-contraction engine: 0 = fp32 CUDA-core tiles, 1 = tcgen05 3xTF32 (TMA + TMEM), 2 = auto
+ * (tcgen05 when the shape fills a 128x256 tile grid).  Returns the previous setting. */
+int gnngp_set_gemm_engine(int engine);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t gnngp_launch_count(void);
+
+/* ---- adjacency: COO -> CSR ---------------------------------------------------------------
+ * Replaces the implicit coalesce ATen runs on the sparse operand of every `A @ X`
+ * (src/compute.py:142,145,...; A built uncoalesced at src/datasets.py:328).  Entries are sorted by
+ * (row, col) with a stable radix sort; duplicates stay adjacent and are summed by the SpMM.
+ * rowptr: int64[n_rows+1], colidx: int32[nnz], vals: float[nnz]. */
+size_t gnngp_csr_from_coo_workspace_bytes(int64_t nnz, int64_t n_rows);
+int gnngp_csr_from_coo(const int64_t *row, const int64_t *col, const float *val, int64_t nnz,
+                       int64_t n_rows, int64_t n_cols, int64_t *rowptr, int32_t *colidx, float *vals,
+                       void *workspace, size_t workspace_bytes, gnngp_stream_t stream);
+
+/* ---- K1: CSR SpMM  C[:, 0:k] = alpha * A @ B ----------------------------------------------
+ * Replaces `sigma_w * A @ Q` (src/compute.py:142,145,164,169,186,205,209) and `A @ (A @ C0).T`
+ * (src/compute.py:132,135,151,156,176,195,198).  B: [n_cols x k] ld ldb, C: [n_rows x k] ld ldc.
+ * tile_cols: width of the column tile kept L2-resident (0 = choose from n_cols; else 32/64/128).
+ * nnz_per_warp: nonzeros per warp work item (0 = default).  Rows that straddle a work item are
+ * combined with fp32 atomics, so C is zero-filled first (the call does that itself). */
+int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals,
+                       int64_t n_rows, int64_t n_cols, int64_t nnz, const float *B, int64_t ldb,
+                       int64_t k, float alpha, float *C, int64_t ldc, int tile_cols, int nnz_per_warp,
+                       gnngp_stream_t stream);
+
+/* ---- dense contractions  D = A * B^T  (A: [M x K] ld lda, B: [N x K] ld ldb) ----------------
+ * Both operands K-contiguous ("NT").  The 3xTF32 engine needs a workspace for the hi/lo operand
+ * split: query it with gnngp_gemm_workspace_bytes(M, N, K). */
+size_t gnngp_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+/* plain: C = alpha * A B^T (+ beta * C).  Replaces `X @ X.T` (src/compute.py:25), `Q @ Q[mask].T`,
+ * `K[~mask] @ V` (src/compute.py:16), `Q[mb].T @ Q[mb]` (src/predict.py:57), `v.T @ (...)`
+ * (src/predict.py:30,60). */
+int gnngp_gemm_nt_f32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
+                      int64_t M, int64_t N, int64_t K, float alpha, float beta,
+                      void *workspace, size_t workspace_bytes, gnngp_stream_t stream);
+
+/* K2: landmark Gram with the ReLU arc-cosine expectation fused into the epilogue.
+ * E[i,j] = J1(clamp((Q_i . L_j) / s_i / t_j)) * s_i * t_j,  J1(c) = (sin th + (pi - th) cos th)/(2 pi),
+ * th = acos c.  Replaces the Gram + 12 elementwise passes of src/compute.py:124-126.
+ * Q: [n x m] rows, L: [n_land x m] landmark rows, s: [n] row norms, t: [n_land] landmark norms. */
+int gnngp_gram_arccos_f32(const float *Q, int64_t ldq, int64_t n, const float *L, int64_t ldl,
+                          int64_t n_land, int64_t m, const float *s, const float *t, float *E,
+                          int64_t lde, void *workspace, size_t workspace_bytes, gnngp_stream_t stream);
+
+/* Initial kernels between the rows of X ([n x f]) and of R ([r x f]) — src/compute.py:24-35, 46-64.
+ * kind: 0 linear, 1 rbf exp(-gamma |x-y|_2^2), 2 sigmoid tanh(gamma x.y + c), 3 polynomial (x.y + c)^d,
+ * 4 arccos 1 - acos(clamp(x.y))/pi (inputs already normalised by the caller).
+ * xx / rr: squared row norms (rbf only, else may be null). */
+int gnngp_initial_kernel_f32(int kind, const float *X, int64_t ldx, int64_t n, const float *R, int64_t ldr,
+                             int64_t r, int64_t f, const float *xx, const float *rr, float gamma, float c,
+                             float d, float *C0, int64_t ldc, void *workspace, size_t workspace_bytes,
+                             gnngp_stream_t stream);
+/* laplacian exp(-gamma |x-y|_1): not a contraction, its own kernel (src/compute.py:28-29, 51-53). */
+int gnngp_laplacian_kernel_f32(const float *X, int64_t ldx, int64_t n, const float *R, int64_t ldr, int64_t r,
+                               int64_t f, float gamma, float *C0, int64_t ldc, gnngp_stream_t stream);
+
+/* K6: posterior means for all nuggets in one contraction, scattered into fitted[G][n][C]:
+ * fitted[g][i][c] = sum_j Q[i][j] * Bt[g*C + c][j].  Replaces the 101-iteration loop of
+ * src/predict.py:31-32 / 61-62.  Bt: [(G*C) x m] ld ldb. */
+int gnngp_nugget_sweep_f32(const float *Q, int64_t ldq, int64_t n, int64_t m, const float *Bt, int64_t ldb,
+                           int64_t G, int64_t C, float *fitted, void *workspace, size_t workspace_bytes,
+                           gnngp_stream_t stream);
+/* S[(g*C + c)][j] = temp[j][c] / (w[j] + eps[g] * d[0])  — the `temp/(w+eps*d)` of src/predict.py:32,62
+ * for every nugget; d is a device scalar.  temp: [m x C] ld ldt, S: [(G*C) x m] ld lds. */
+int gnngp_nugget_coeff_f32(const float *temp, int64_t ldt, const float *w, const float *eps, const float *d,
+                           int64_t m, int64_t C, int64_t G, float *S, int64_t lds, gnngp_stream_t stream);
+
+/* ---- row / column utilities -------------------------------------------------------------- */
+/* out[i] = sum_j Q[i][j]^2 (take_sqrt = 0) or its square root (1) — src/compute.py:124, src/predict.py:58. */
+int gnngp_row_sumsq_f32(const float *Q, int64_t ldq, int64_t n, int64_t m, int take_sqrt, float *out,
+                        gnngp_stream_t stream);
+/* out[0] = mean(v[0:n]) or, stride > 1, the mean of v[0], v[stride], ... (diagonal: stride = ld + 1). */
+int gnngp_mean_f32(const float *v, int64_t n, int64_t stride, float *out, gnngp_stream_t stream);
+/* M[i][col] = value for every row — the bias column `Q[:,-1] = sigma_b` (src/compute.py:142,145). */
+int gnngp_fill_col_f32(float *M, int64_t ld, int64_t n, float value, gnngp_stream_t stream);
+/* dst[r][:] = src[idx[r]][:]  — boolean-mask row gathers `Q[mask]`, `K[mask]` (src/compute.py:11,125). */
+int gnngp_gather_rows_f32(const float *src, int64_t lds, const int64_t *idx, int64_t n_idx, int64_t ncols,
+                          float *dst, int64_t ldd, gnngp_stream_t stream);
+/* dst[idx[r]][:] = src[r][:] — `Q[mask] = ...` (src/compute.py:15). */
+int gnngp_scatter_rows_f32(const float *src, int64_t lds, const int64_t *idx, int64_t n_idx, int64_t ncols,
+                           float *dst, int64_t ldd, gnngp_stream_t stream);
+/* dst[c][r] = src[idx[r]][c] (idx may be null = identity): `Q[mb].T`, `(A @ C0).T`, `K[:,mb]`. */
+int gnngp_gather_rows_transposed_f32(const float *src, int64_t lds, const int64_t *idx, int64_t n_idx,
+                                     int64_t ncols, float *dst, int64_t ldd, gnngp_stream_t stream);
+/* dst[i][j] = src[i][idx[j]] — column gather `K[mb][:,mb]`, `K[:,mb]` (src/predict.py:27,32). */
+int gnngp_gather_cols_f32(const float *src, int64_t lds, int64_t n, const int64_t *idx, int64_t n_idx,
+                          float *dst, int64_t ldd, gnngp_stream_t stream);
+/* out = a*x + b*y + c elementwise over an [n x m] block (y may be null); in-place allowed. */
+int gnngp_affine_f32(float *out, int64_t ldo, const float *x, int64_t ldx, const float *y, int64_t ldy,
+                     int64_t n, int64_t m, float a, float b, float c, gnngp_stream_t stream);
+
+/* ---- Nystrom square root pieces (src/compute.py:6-17) ------------------------------------ */
+/* root[j] = sqrt(max(D[j],0)); inv[j] = root[j] / max(D[j], 1e-4 * D[n-1])  (D ascending). */
+int gnngp_nystrom_spectrum_f32(const float *D, int64_t n, float *root, float *inv, gnngp_stream_t stream);
+/* out[i][j] = V[i][j] * d[j]   (transpose = 0)   or   out[j][i] = V[i][j] * d[j]   (transpose = 1). */
+int gnngp_scale_cols_f32(const float *V, int64_t ldv, int64_t n, int64_t m, const float *d, int transpose,
+                         float *out, int64_t ldo, gnngp_stream_t stream);
+
+/* ---- exact path: g(K) on a dense kernel (src/compute.py:110-117) --------------------------
+ * E[i][j] = J1(clamp(K[i][j] / s_i / s_j)) s_i s_j with s = sqrt(diag K); E may alias K. */
+int gnngp_arccos_dense_f32(const float *K, int64_t ldk, int64_t n, float *E, int64_t lde, float *s_scratch,
+                           gnngp_stream_t stream);
+
+/* ---- targets and metrics (src/predict.py:23-25, 53-55, 66-90) ----------------------------- */
+/* Yt[c][r] = (y[idx[r]] == c) — transposed one-hot of the training labels. */
+int gnngp_onehot_t_f32(const int64_t *y, const int64_t *idx, int64_t n_idx, int64_t C, float *Yt, int64_t ldy,
+                       gnngp_stream_t stream);
+/* K7 classification: counts[g][s] = #{ i : membership[i] has bit s, argmax_c fitted[g][i][c] == y[i] }.
+ * membership: uint8 bit set per node (bit s = node belongs to subset s, up to 8 subsets). counts int32 [G x 8],
+ * zeroed by the call. */
+int gnngp_argmax_count(const float *fitted, const int64_t *y, const uint8_t *membership, int64_t G, int64_t n,
+                       int64_t C, int32_t *counts, gnngp_stream_t stream);
+/* K7 regression: sse[g][s] = sum over subset s of sum_k (fitted[g][i][k] - y[i][k])^2 (double [G x 8]). */
+int gnngp_sqerr_sum(const float *fitted, const float *y, const uint8_t *membership, int64_t G, int64_t n,
+                    int64_t k, double *sse, gnngp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNGP_B200_H_ */

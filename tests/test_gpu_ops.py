@@ -1,0 +1,234 @@
+"""Operator-level parity on the B200: every C-ABI kernel against the same operator restated in plain
+torch on the CPU (tests/stub_ops.py) on seeded inputs, including ragged / empty / misaligned shapes."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from stub_ops import StubOps
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5   # fp32 kernels vs fp32 torch: relative Frobenius
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gnngp_b200.ops import default_ops
+    o = default_ops()
+    o.set_gemm_engine(0)      # fp32 CUDA-core tiles; the tcgen05 engine has its own test file
+    yield o
+    o.set_gemm_engine(2)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return StubOps()
+
+
+def rel(a, b):
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def rand_graph(n, nnz, seed, hub=None, empty_rows=()):
+    g = torch.Generator().manual_seed(seed)
+    row = torch.randint(0, n, (nnz,), generator=g)
+    col = torch.randint(0, n, (nnz,), generator=g)
+    if hub is not None:            # one very long row, like the power-law hubs of the Reddit shape
+        row[: nnz // 3] = hub
+    for r in empty_rows:
+        row[row == r] = (r + 1) % n
+    val = torch.randn(nnz, generator=g)
+    return row, col, val
+
+
+@pytest.mark.parametrize("n,nnz,hub", [(64, 400, None), (1000, 30000, 7), (5000, 200000, 123), (300, 0, None)])
+def test_csr_from_coo_and_spmm(ops, ref, n, nnz, hub):
+    row, col, val = rand_graph(n, nnz, seed=n + nnz, hub=hub, empty_rows=(0, n - 1))
+    csr = ops.csr_from_coo(row.cuda(), col.cuda(), val.cuda(), n, n)
+    rp = csr.rowptr.cpu()
+    assert rp[0] == 0 and rp[-1] == nnz and bool((rp[1:] >= rp[:-1]).all())
+    counts = torch.bincount(row, minlength=n) if nnz else torch.zeros(n, dtype=torch.long)
+    assert torch.equal(rp[1:] - rp[:-1], counts)
+    if nnz:
+        # sorted by (row, col), values carried along
+        rows_sorted = torch.repeat_interleave(torch.arange(n), counts)
+        key = rows_sorted * n + csr.colidx.cpu().long()
+        assert bool((key[1:] >= key[:-1]).all())
+        dense = torch.zeros(n, n, dtype=torch.float64)
+        dense.index_put_((rows_sorted, csr.colidx.cpu().long()), csr.vals.cpu().double(), accumulate=True)
+        want = torch.zeros(n, n, dtype=torch.float64)
+        want.index_put_((row, col), val.double(), accumulate=True)
+        assert torch.allclose(dense, want, atol=1e-6)
+    cref = ref.csr_from_coo(row, col, val, n, n)
+    for k in (1, 3, 32, 37, 64, 130, 257):
+        g = torch.Generator().manual_seed(k)
+        b = torch.randn(n, k, generator=g)
+        want = ref.spmm(cref, b, 0.7)
+        got = ops.spmm(csr, b.cuda(), 0.7)
+        assert got.shape == want.shape
+        assert rel(got, want) < TOL or float(want.norm()) == 0.0, (n, nnz, k, rel(got, want))
+
+
+@pytest.mark.parametrize("tile,chunk", [(32, 32), (64, 64), (128, 256), (0, 0)])
+def test_spmm_tiles_alignment_and_strided_output(ops, ref, tile, chunk):
+    n = 3000
+    row, col, val = rand_graph(n, 150000, seed=5, hub=11)
+    csr = ops.csr_from_coo(row.cuda(), col.cuda(), val.cuda(), n, n)
+    cref = ref.csr_from_coo(row, col, val, n, n)
+    ops.spmm_tile_cols, ops.spmm_nnz_per_warp = tile, chunk
+    try:
+        for k, pad in ((602, 0), (602, 2), (301, 3), (129, 3), (200, 56)):
+            g = torch.Generator().manual_seed(k + pad)
+            store = torch.randn(n, k + pad, generator=g)
+            b = store[:, :k]                        # leading dimension k + pad: 16 B / 8 B / 4 B aligned rows
+            want = ref.spmm(cref, b.contiguous(), 1.3)
+            big = torch.full((n, k + 9), 7.0).cuda()
+            got = ops.spmm(csr, b.cuda() if pad == 0 else store.cuda()[:, :k], 1.3, out=big[:, 5:5 + k])
+            assert rel(got, want) < TOL, (tile, chunk, k, pad, rel(got, want))
+            assert bool((big[:, :5] == 7.0).all()) and bool((big[:, 5 + k:] == 7.0).all()), "wrote outside the view"
+    finally:
+        ops.spmm_tile_cols, ops.spmm_nnz_per_warp = 0, 0
+
+
+def test_spmm_duplicates_are_summed(ops):
+    row = torch.tensor([0, 0, 0, 2, 2]); col = torch.tensor([1, 1, 3, 0, 0]); val = torch.tensor([1., 2., 4., 8., 16.])
+    csr = ops.csr_from_coo(row.cuda(), col.cuda(), val.cuda(), 4, 4)
+    b = torch.eye(4).cuda()
+    got = ops.spmm(csr, b).cpu()
+    want = torch.zeros(4, 4); want[0, 1] = 3; want[0, 3] = 4; want[2, 0] = 24
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 7, 3), (128, 128, 16), (130, 257, 70), (513, 300, 1031), (64, 2000, 257)])
+def test_gemm_nt_simt(ops, ref, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    got = ops.gemm_nt(a.cuda(), b.cuda(), alpha=0.5)
+    assert rel(got, 0.5 * a @ b.T) < TOL
+    # strided operands / output view, beta accumulate
+    big = torch.randn(M, N + 6, generator=g)
+    out = big.cuda()
+    ops.gemm_nt(a.cuda(), b.cuda(), alpha=2.0, out=out[:, 3:3 + N], beta=1.0)
+    want = big.clone(); want[:, 3:3 + N] += 2.0 * a @ b.T
+    assert rel(out, want) < TOL
+
+
+def test_gram_arccos_and_dense_arccos(ops, ref):
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(700, 45, generator=g)
+    idx = torch.randperm(700, generator=g)[:130].sort().values
+    l = q[idx]
+    s, t = ref.row_norms(q), ref.row_norms(l)
+    got = ops.gram_arccos(q.cuda(), l.cuda(), ops.row_norms(q.cuda()), ops.row_norms(l.cuda()))
+    want = ref.gram_arccos(q, l, s, t)
+    assert rel(got, want) < TOL
+    # the landmark block must be symmetric to rounding and have s_i^2 / 2 on its diagonal (J1(0) = 1/2)
+    blk = got.cpu()[idx]
+    assert rel(blk, blk.T) < 1e-6
+    assert torch.allclose(torch.diag(blk), 0.5 * t * t, rtol=2e-5)
+    k = (q[:300] @ q[:300].T)
+    got = ops.arccos_dense(k.cuda())
+    assert rel(got, ref.arccos_dense(k)) < TOL
+    # in place
+    kk = k.cuda()
+    ops.arccos_dense(kk, out=kk)
+    assert rel(kk, ref.arccos_dense(k)) < TOL
+
+
+def test_arccos_nan_semantics_match_reference(ops):
+    """A zero-norm row gives 0/0 = NaN in the reference (src/compute.py:125): propagated, not masked."""
+    q = torch.randn(40, 6); q[3] = 0
+    l = q[[1, 3, 5]]
+    got = ops.gram_arccos(q.cuda(), l.cuda(), ops.row_norms(q.cuda()), ops.row_norms(l.cuda())).cpu()
+    assert bool(torch.isnan(got[3]).all()) and bool(torch.isnan(got[:, 1]).all())
+    assert not bool(torch.isnan(got[[0, 1, 2, 4]][:, [0, 2]]).any())
+
+
+@pytest.mark.parametrize("kind,params", [("linear", {}), ("rbf", dict(gamma=0.01)), ("laplacian", dict(gamma=0.02)),
+                                         ("sigmoid", dict(gamma=0.01, c=0.1)), ("polynomial", dict(c=1.0, d=2.0)),
+                                         ("polynomial", dict(c=5.0, d=3.0))])
+def test_initial_kernels(ops, ref, kind, params):
+    g = torch.Generator().manual_seed(2)
+    x, r = torch.randn(333, 41, generator=g), torch.randn(77, 41, generator=g)
+    got = ops.initial_kernel(kind, x.cuda(), r.cuda(), **params)
+    assert rel(got, ref.initial_kernel(kind, x, r, **params)) < 5e-5
+    xn, rn = x / x.norm(dim=1, keepdim=True), r / r.norm(dim=1, keepdim=True)
+    assert rel(ops.initial_kernel("arccos", xn.cuda(), rn.cuda()), ref.initial_kernel("arccos", xn, rn)) < 5e-5
+
+
+def test_row_and_column_utilities(ops, ref):
+    g = torch.Generator().manual_seed(3)
+    m = torch.randn(501, 67, generator=g)
+    idx = torch.randperm(501, generator=g)[:120].sort().values
+    cidx = torch.randperm(67, generator=g)[:20].sort().values
+    mc = m.cuda()
+    assert rel(ops.row_norms(mc), ref.row_norms(m)) < 1e-6
+    assert rel(ops.row_norms(mc, sqrt=False), ref.row_norms(m, sqrt=False)) < 1e-6
+    assert abs(float(ops.mean(ops.row_norms(mc))) - float(ref.row_norms(m).mean())) < 1e-5
+    sq = torch.randn(90, 90, generator=g)
+    assert abs(float(ops.diag_mean(sq.cuda())) - float(torch.diag(sq).mean())) < 1e-6
+    assert torch.equal(ops.gather_rows(mc, idx.cuda()).cpu(), m[idx])
+    assert torch.equal(ops.gather_rows_t(mc, idx.cuda()).cpu(), m[idx].T)
+    assert torch.equal(ops.transpose(mc).cpu(), m.T)
+    assert torch.equal(ops.gather_cols(mc, cidx.cuda()).cpu(), m[:, cidx])
+    dst = torch.zeros(501, 67).cuda()
+    ops.scatter_rows(dst, idx.cuda(), ops.gather_rows(mc, idx.cuda()))
+    want = torch.zeros(501, 67); want[idx] = m[idx]
+    assert torch.equal(dst.cpu(), want)
+    q = torch.zeros(501, 68).cuda()[:, :67]
+    ops.fill_col(q, 66, 0.25)
+    assert bool((q[:, 66] == 0.25).all()) and float(q[:, :66].abs().sum()) == 0.0
+    y = torch.randn(501, 67, generator=g)
+    out = ops.empty(501, 67, mc.device)
+    ops.affine(out, mc, y.cuda(), 0.3, -1.5, 2.0)
+    assert rel(out, 0.3 * m - 1.5 * y + 2.0) < 1e-6
+    ops.affine(out, mc, None, 2.0, 0.0, 0.0)
+    assert rel(out, 2.0 * m) < 1e-7
+    d = torch.randn(67, generator=g)
+    assert rel(ops.scale_cols(mc, d.cuda()), m * d) < 1e-7
+    assert rel(ops.scale_cols(mc, d.cuda(), transpose=True), (m * d).T) < 1e-7
+    ev = torch.sort(torch.randn(64, generator=g)).values
+    ev[:5] = torch.tensor([-1e-3, -1e-6, 0.0, 1e-7, 1e-5])
+    ev = torch.sort(ev).values
+    r1, i1 = ops.nystrom_spectrum(ev.cuda())
+    r2, i2 = ref.nystrom_spectrum(ev)
+    assert rel(r1, r2) < 1e-7 and rel(i1, i2) < 1e-6
+
+
+def test_targets_sweep_and_metrics(ops, ref):
+    g = torch.Generator().manual_seed(4)
+    n, m, C, G = 400, 33, 5, 7
+    y = torch.randint(0, C, (n,), generator=g)
+    idx = torch.randperm(n, generator=g)[:150].sort().values
+    assert torch.equal(ops.onehot_t(y.cuda(), idx.cuda(), C).cpu(), ref.onehot_t(y, idx, C))
+    temp = torch.randn(m, C, generator=g)
+    w = torch.rand(m, generator=g) + 0.1
+    eps = torch.logspace(-3, 1, G)
+    d = torch.tensor([1.7])
+    s1 = ops.nugget_coeff(temp.cuda(), w.cuda(), eps.cuda(), d.cuda())
+    assert rel(s1, ref.nugget_coeff(temp, w, eps, d)) < 1e-6
+    q = torch.randn(n, m, generator=g)
+    bt = torch.randn(G * C, m, generator=g)
+    f1 = ops.nugget_sweep(q.cuda(), bt.cuda(), G, C)
+    f2 = ref.nugget_sweep(q, bt, G, C)
+    assert f1.shape == (G, n, C) and rel(f1, f2) < TOL
+    member = torch.randint(0, 8, (n,), generator=g).to(torch.uint8)
+    f2[1, 5, :] = f2[1, 5, 0]                    # exact tie -> first index, like torch.argmax
+    f2[2, 9, 3] = float("nan")                   # NaN is maximal for torch.argmax
+    c1 = ops.argmax_count(f2.cuda(), y.cuda(), member.cuda()).cpu()
+    assert torch.equal(c1, ref.argmax_count(f2, y, member))
+    yr = torch.randn(n, generator=g)
+    fr = torch.randn(G, n, generator=g)
+    e1 = ops.sqerr_sum(fr.cuda(), yr.cuda(), member.cuda()).cpu()
+    assert torch.allclose(e1, ref.sqerr_sum(fr, yr, member), rtol=1e-9)
+
+
+def test_cpu_tensors_are_rejected(ops):
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.row_norms(torch.randn(4, 4))
+    with pytest.raises(RuntimeError):
+        ops.gemm_nt(torch.randn(4, 4).cuda(), torch.randn(4, 5).cuda())
