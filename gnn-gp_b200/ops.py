@@ -130,13 +130,18 @@ class CudaOps(object):
         key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index)
         hit = self._csr_cache.get(key)
         if hit is None:
-            if val.dtype != torch.float32:
-                val = val.to(torch.float32)
-            hit = self.csr_from_coo(idx[0], idx[1], val, A.shape[0], A.shape[1])
-            if len(self._csr_cache) > 8:
+            csr = self.csr_from_coo(idx[0], idx[1], val if val.dtype == torch.float32 else val.to(torch.float32),
+                                    A.shape[0], A.shape[1])
+            if len(self._csr_cache) >= 2:
                 self._csr_cache.clear()
+            # the entry keeps the COO tensors alive, so their addresses cannot be recycled for other data
+            # while the key is in the cache (in-place edits of A's values are not tracked)
+            hit = (csr, idx, val)
             self._csr_cache[key] = hit
-        return hit
+        return hit[0]
+
+    def clear_cache(self) -> None:
+        self._csr_cache.clear()
 
     # ------------------------------------------------------------------ K1 SpMM
     def spmm(self, csr: CsrMatrix, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
