@@ -30,9 +30,11 @@ SHAPES: Dict[str, dict] = {
     # configs[2]: chameleon-shape (regression), 36 101 directed edges
     "chameleon": dict(n=2277, und=31400, f=3132, c=0, split=(1092, 729, 456), feat="bow"),
     # configs[3]: ogbn-arxiv-shape, 1.17 M directed edges symmetrised
-    "arxiv": dict(n=169343, und=1166243, f=128, c=40, split=(90941, 29799, 48603), feat="gauss"),
+    "arxiv": dict(n=169343, und=1166243, f=128, c=40, split=(90941, 29799, 48603), feat="gauss", sep=0.25, p_same=0.6,
+                  exact_edges=True, label_noise=0.08),
     # configs[4]: Reddit-shape, 114.6 M directed edges
-    "reddit": dict(n=232965, und=57307946, f=602, c=41, split=(153431, 23831, 55703), feat="gauss"),
+    "reddit": dict(n=232965, und=57307946, f=602, c=41, split=(153431, 23831, 55703), feat="gauss", sep=0.1, p_same=0.5,
+                   exact_edges=True, label_noise=0.06),
     # tiny shapes for unit tests / smoke
     "tiny": dict(n=257, und=1100, f=40, c=4, split=(120, 60, 77), feat="gauss", sep=0.3, p_same=0.5),
     "tiny-reg": dict(n=203, und=900, f=24, c=0, split=(100, 50, 53), feat="gauss", sep=0.5, p_same=0.6),
@@ -88,6 +90,19 @@ def make_graph(shape: str = "tiny", seed: int = 0, device: Optional[torch.device
     lo = torch.minimum(src[keep], dst[keep])
     hi = torch.maximum(src[keep], dst[keep])
     key = torch.unique(lo * n + hi)
+    if spec.get("exact_edges"):
+        # hub-heavy shapes lose many draws to duplicates: top up until the undirected edge count is reached
+        rounds = 0
+        while key.numel() < und and rounds < 12:
+            extra = int((und - key.numel()) * 1.3) + 1024
+            s2 = _powerlaw_endpoints(n, extra, power, gen, device)
+            d2 = torch.where(torch.rand(extra, generator=gen, device=device) < p_same,
+                             order[starts[label[s2]] + torch.minimum((torch.rand(extra, generator=gen, device=device, dtype=torch.float64)
+                                                                      * counts[label[s2]].to(torch.float64)).long(), counts[label[s2]] - 1)],
+                             torch.randint(0, n, (extra,), generator=gen, device=device))
+            ok = s2 != d2
+            key = torch.unique(torch.cat([key, torch.minimum(s2[ok], d2[ok]) * n + torch.maximum(s2[ok], d2[ok])]))
+            rounds += 1
     if key.numel() > und:
         pick = torch.randperm(key.numel(), generator=gen, device=device)[:und]
         key = key[pick]
@@ -112,6 +127,10 @@ def make_graph(shape: str = "tiny", seed: int = 0, device: Optional[torch.device
     # targets
     if c > 0:
         y = label.clone()
+        noise = spec.get("label_noise", 0.0)
+        if noise > 0:     # observed labels differ from the planted community for a fraction of nodes
+            flip = torch.rand(n, generator=gen, device=device) < noise
+            y = torch.where(flip, torch.randint(0, c, (n,), generator=gen, device=device), y)
     else:
         level = torch.randn(groups, generator=gen, device=device)
         y = (level[label] + 0.5 * torch.randn(n, generator=gen, device=device)).to(torch.float32)

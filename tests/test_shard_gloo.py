@@ -1,0 +1,88 @@
+"""The row-sharded orchestration (gnngp_b200/shard.py + pipeline.py collectives) under world_size 2
+and 3 with the gloo backend on CPU, driven by the test-only CPU operator stand-in, against the same
+pipeline on one rank.  The CUDA kernels are not involved here; the NCCL path is measured by bench.py."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import cases
+    from stub_ops import StubOps
+    from gnngp_b200.shard import ShardedGNNGP
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    model = ShardedGNNGP(data, device=None, Nystrom=True, ops=StubOps())
+    model.mask["landmark"] = masks["landmark"]
+    model.set_hyper_param(case["L"], case["sigma_b"], case["sigma_w"], initial=case["initial"], method=case["method"],
+                          **case["params"])
+    model.predict(nugget)
+    fit = model.gather_fit()
+    q_full = model.comm.all_gather_rows(model.Q, model.layout)
+    summ = model.get_summary()
+    if rank == 0:
+        torch.save({"fit": fit, "Q": q_full.clone(), "result": model.result,
+                    "summary": {k: float(summ[k]) for k in ("nugget", "train", "val", "test")},
+                    "rows": (model.layout.begin, model.layout.end)}, os.path.join(out_dir, "rank0.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name", [(2, "tiny-GCN-nys2-L3"), (2, "tiny-SAGE-nys2-L2"), (3, "tiny-GCN2-nys2-L2"),
+                                        (2, "tinyreg-GIN-nys1-L3"), (2, "tiny-GCN-nys8-L2"), (2, "tiny-GCN-nys2-arccos")])
+def test_sharded_matches_single_rank(tmp_path, world, name):
+    import cases
+    import runner
+    from stub_ops import StubOps
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    ref = runner.run_pipeline(StubOps(), case, data, masks, nugget)
+    kq, kr = got["Q"] @ got["Q"].T, ref["Q"] @ ref["Q"].T
+    assert float((kq - kr).norm() / kr.norm()) < 1e-4
+    assert got["fit"].shape == ref["fit"].shape
+    assert float((got["fit"][50] - ref["fit"][50]).norm() / ref["fit"][50].norm()) < 1e-3
+    for key in ("train", "val", "test", "landmark"):
+        assert float((got["result"][key] - ref["result"][key]).abs().max()) < 0.03
+    # against the reference's golden outputs too
+    runner.check_against_golden(name, {"Q": got["Q"], "fit": got["fit"], "result": got["result"]}, masks)
+
+
+def test_row_layout_partitions_every_row_once():
+    from gnngp_b200.pipeline import RowLayout
+    for n in (1, 7, 257, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [(RowLayout(n, world, r).begin, RowLayout(n, world, r).end) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            mask = torch.zeros(n, dtype=torch.bool)
+            mask[::3] = True
+            pos_all = []
+            for r in range(world):
+                rows, pos, count = RowLayout(n, world, r).local_index(mask)
+                assert count == int(mask.sum())
+                pos_all.append(pos)
+                assert bool(mask[rows + RowLayout(n, world, r).begin].all())
+            assert torch.equal(torch.cat(pos_all), torch.arange(int(mask.sum())))
