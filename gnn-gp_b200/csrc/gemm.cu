@@ -17,16 +17,18 @@ static bool use_tensor_cores(int64_t M, int64_t N, int64_t K)
 {
     const int engine = g_gemm_engine.load();
     if (engine == 0 || K <= 0) return false;
-    if (engine == 1) return true;
+    if (engine == 1 || engine == 3) return true;
     // auto: enough 128x256 tiles to occupy a good part of the chip and a K loop worth pipelining
-    return ceil_div(M, tc::BM) * ceil_div(N, tc::BN) >= 32 && K >= 128;
+    return ceil_div(M, tc::v2::BM) * ceil_div(N, tc::v2::BN) >= 64 && K >= 128;
 }
 
 template <class Epi>
 static int contract(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                     const Epi &epi, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    if (use_tensor_cores(M, N, K)) return tc::gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, ws, ws_bytes, st);
+    // engine 3 = the unchunked 128x256 tcgen05 kernel (faster, but its long TMEM accumulation is biased:
+    // kept for measurement only); engines 1 / 2 use the chunked-accumulation kernel
+    if (use_tensor_cores(M, N, K)) return tc::gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, ws, ws_bytes, st, g_gemm_engine.load() != 3);
     return gemm_nt_simt(A, lda, B, ldb, M, N, K, epi, st);
 }
 

@@ -286,6 +286,169 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
 }
 
+// =============================================================================================
+// v2: chunked accumulation (the default tensor-core engine)
+//
+// Measured on B200: tcgen05.mma adds into the TMEM accumulator with truncation, so a long K loop
+// accumulates a bias of ~0.5 ulp(acc) per MMA (2e-5 relative at K = 3 070, 1.7e-3 for the train Gram
+// with K = N_t = 153 k) — far above the fp32 reference.  v2 keeps each TMEM partial sum short
+// (CHUNK_KB k-blocks = 64 K-elements = 24 MMAs, starting from zero) and lets the epilogue warps add the
+// partials into a 128-column fp32 master accumulator held in REGISTERS with round-to-nearest adds.
+// Tile 128 x 128 so that one thread's master row fits the register file; four 128-column TMEM partial
+// buffers (all 512 columns) keep the MMA issuer up to four chunks ahead of the epilogue, which hides
+// the fused epilogue (arc-cosine / scatter) of the previous tile.
+namespace v2 {
+
+constexpr int BM = 128, BN = 128;
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * BK * 4;
+constexpr int B_BYTES = BN * BK * 4;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int PARTIALS = 4;                                            // 4 x 128 TMEM columns
+constexpr int CHUNK_KB = 2;                                            // k-blocks per partial sum
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, Epi epi)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + PARTIALS + a); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * PARTIALS));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < PARTIALS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t total = tiles_m * tiles_n;
+    const int chunks = (k_blocks + CHUNK_KB - 1) / CHUNK_KB;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const TileCoord tc_ = raster(tile, tiles_m, tiles_n);
+                const int32_t m0 = (int32_t)(tc_.m_blk * BM), n0 = (int32_t)(tc_.n_blk * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t dst = base + stage * STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(dst + A_BYTES, &map_a_lo, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(dst + 2 * A_BYTES, &map_b_hi, full_bar(stage), kb * BK, n0);
+                    tma_load_2d(dst + 2 * A_BYTES + B_BYTES, &map_b_lo, full_bar(stage), kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer: one short partial sum per chunk, round-robin over the TMEM buffers =====
+            int stage = 0, part = 0;
+            uint32_t phase = 0, part_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(tempty_bar(part), part_phase ^ 1u);
+                    fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(part * BN);
+                    const int kb_end = min(k_blocks, (ch + 1) * CHUNK_KB);
+                    for (int kb = ch * CHUNK_KB; kb < kb_end; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        fence_after();
+                        const uint32_t a_hi = base + stage * STAGE_BYTES;
+                        const uint32_t a_lo = a_hi + A_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                        const uint32_t b_lo = b_hi + B_BYTES;
+                        const bool first_kb = (kb == ch * CHUNK_KB);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t off = k * UMMA_K * 4;
+                            const uint64_t dah = smem_desc(a_hi + off), dal = smem_desc(a_lo + off);
+                            const uint64_t dbh = smem_desc(b_hi + off), dbl = smem_desc(b_lo + off);
+                            // small terms first, so they are not absorbed by a large running sum
+                            umma_tf32(tmem_d, dal, dbh, kInstrDesc, (first_kb && k == 0) ? 0u : 1u);
+                            umma_tf32(tmem_d, dah, dbl, kInstrDesc, 1u);
+                            umma_tf32(tmem_d, dah, dbh, kInstrDesc, 1u);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(tfull_bar(part));
+                    if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps: master accumulator in registers, RN adds of the TMEM partial sums =====
+        const int wq = warp - 4;
+        int part = 0;
+        uint32_t part_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const TileCoord tc_ = raster(tile, tiles_m, tiles_n);
+            float master[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) master[j] = 0.0f;
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait(tfull_bar(part), part_phase);
+                fence_after();
+#pragma unroll
+                for (int cc = 0; cc < BN / 32; ++cc) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(part * BN + cc * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) master[cc * 32 + j] += v[j];
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(part));
+                if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
+            }
+            const int64_t row = tc_.m_blk * BM + wq * 32 + lane;
+            const int64_t col0 = tc_.n_blk * BN;
+            if (row < M) {
+                if (epi.vec_ok && col0 + BN <= N) {
+#pragma unroll
+                    for (int j = 0; j < BN; j += 4) epi.vec4(row, col0 + j, master[j], master[j + 1], master[j + 2], master[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN; ++j)
+                        if (col0 + j < N) epi(row, col0 + j, master[j]);
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace v2
+
 // ---- operand split -----------------------------------------------------------------------
 // hi/lo: [rows x Kp] with Kp = round_up(K, 32); padding columns are written as zeros.
 __global__ void split_tf32_kernel(const float *__restrict__ src, int64_t ld, int64_t rows, int64_t K, int64_t Kp,
@@ -363,7 +526,7 @@ inline size_t workspace_bytes(int64_t M, int64_t N, int64_t K)
 
 template <class Epi>
 static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                      const Epi &epi, void *workspace, size_t ws_bytes, cudaStream_t st)
+                      const Epi &epi, void *workspace, size_t ws_bytes, cudaStream_t st, bool chunked = true)
 {
     if (M <= 0 || N <= 0) return GNNGP_OK;
     GNNGP_REQUIRE(K > 0, "tcgen05 gemm: K must be positive");
@@ -389,10 +552,25 @@ static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, 
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
+    const int bn = chunked ? v2::BN : BN;
     if ((rc = make_map(&ma_hi, a_hi, M, Kp, BM)) != GNNGP_OK) return rc;
     if ((rc = make_map(&ma_lo, a_lo, M, Kp, BM)) != GNNGP_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, N, Kp, BN)) != GNNGP_OK) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, N, Kp, BN)) != GNNGP_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, Kp, bn)) != GNNGP_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, N, Kp, bn)) != GNNGP_OK) return rc;
+
+    if (chunked) {
+        const int64_t tiles_m = ceil_div(M, v2::BM), tiles_n = ceil_div(N, v2::BN);
+        const int grid = (int)std::min<int64_t>(tiles_m * tiles_n, sm_count());
+        auto kernel2 = v2::gemm_nt_tc2_kernel<Epi>;
+        static bool configured2 = false;
+        if (!configured2) {
+            GNNGP_CUDA(cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+            configured2 = true;
+        }
+        kernel2<<<grid, THREADS, v2::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
+        GNNGP_LAUNCHED();
+        return GNNGP_OK;
+    }
 
     const int64_t tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
     const int64_t total = tiles_m * tiles_n;

@@ -16,8 +16,9 @@
 //    ceil(k / TW) times from HBM; B and C move once.
 //  * gathers are 128-bit per lane (VEC = 4) whenever B's base and leading dimension allow it;
 //    SPLIT sub-warps process SPLIT nonzeros per step so a 64-column tile still uses 16-byte loads.
-//    (colidx, vals) are loaded 32 at a time, coalesced, and broadcast with shuffles; four gathers
-//    are in flight per lane before the FMAs.
+//    (colidx, vals) are loaded 32 at a time, coalesced; one lane per nonzero turns the column id into
+//    the byte offset of the B row and stages {offset, value} in shared memory, from where every lane
+//    fetches it with one broadcast LDS.128; four gathers are in flight per lane before the FMAs.
 //  * columns beyond the last full tile go through the scalar, bounds-checked instantiation.
 #include "common.cuh"
 
@@ -58,6 +59,13 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
 {
     constexpr int LANES = 32 / SPLIT;
     constexpr int TW = LANES * VEC;
+    constexpr int GROUP = kUnroll * SPLIT;             // nonzeros consumed per unrolled step
+    // per-warp staging of 32 nonzeros as {byte offset of the B row (64 bit), value}: the offset is
+    // computed once per nonzero by one lane and broadcast with a single LDS.128, instead of two
+    // shuffles and a 64-bit multiply in every lane
+    __shared__ int4 staged[kWarpsPerBlock][32];
+    int4 *stage = staged[threadIdx.x >> 5];
+
     const int lane = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (item >= n_chunks * n_tiles) return;
@@ -66,6 +74,8 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
     const int sub = lane / LANES;
     const int64_t mycol = col_begin + tile * TW + (int64_t)(lane % LANES) * VEC;
     const bool col_ok = CHECK ? (mycol < col_end) : true;   // CHECK is only instantiated with VEC == 1
+    const char *bcol = reinterpret_cast<const char *>(B + mycol);
+    const int64_t row_bytes = ldb * (int64_t)sizeof(float);
 
     const int64_t p0 = piece * chunk;
     const int64_t p1 = min(p0 + chunk, nnz);
@@ -90,38 +100,44 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
 
         for (int64_t q = p; q < seg_end; q += 32) {
             const int64_t mine = q + lane;
-            int32_t c = 0;
-            float v = 0.0f;
+            int4 entry = make_int4(0, 0, 0, 0);
             if (mine < seg_end) {
-                c = __ldcs(colidx + mine);
-                v = __ldcs(vals + mine);
+                const int64_t off = (int64_t)__ldcs(colidx + mine) * row_bytes;
+                entry.x = (int)(uint32_t)off;
+                entry.y = (int)(off >> 32);
+                entry.z = __float_as_int(__ldcs(vals + mine));
             }
+            __syncwarp();
+            stage[lane] = entry;
+            __syncwarp();
             const int cnt = (int)min((int64_t)32, seg_end - q);
-            for (int j = 0; j < cnt; j += kUnroll * SPLIT) {
-                int32_t cc[kUnroll];
-                float vv[kUnroll];
+            const int full = cnt - cnt % GROUP;
+            for (int j = 0; j < full; j += GROUP) {
+                int4 ent[kUnroll];
                 float b[kUnroll][VEC];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int jj = j + u * SPLIT + sub;
-                    cc[u] = __shfl_sync(0xffffffffu, c, jj & 31);
-                    vv[u] = __shfl_sync(0xffffffffu, v, jj & 31);
-                    if (jj >= cnt) vv[u] = 0.0f;
-                }
+                for (int u = 0; u < kUnroll; ++u) ent[u] = stage[j + u * SPLIT + sub];
+                if (col_ok) {
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int jj = j + u * SPLIT + sub;
-                    if (jj < cnt && col_ok) {
-                        load_row<VEC>(B + (int64_t)cc[u] * ldb + mycol, b[u]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) b[u][e] = 0.0f;
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const int64_t off = ((int64_t)ent[u].y << 32) | (uint32_t)ent[u].x;
+                        load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b[u]);
                     }
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(__int_as_float(ent[u].z), b[u][e], acc[e]);
                 }
+            }
+            for (int j = full + sub; j < cnt; j += SPLIT) {          // ragged tail of the batch
+                const int4 ent = stage[j];
+                if (col_ok) {
+                    float b[VEC];
+                    const int64_t off = ((int64_t)ent.y << 32) | (uint32_t)ent.x;
+                    load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b);
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[e] = fmaf(vv[u], b[u][e], acc[e]);
+                    for (int e = 0; e < VEC; ++e) acc[e] = fmaf(__int_as_float(ent.z), b[e], acc[e]);
+                }
             }
         }
         if constexpr (SPLIT == 2) {
@@ -184,17 +200,16 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
     if (aligned(B, 16) && ldb % 4 == 0) vec = 4;
     else if (aligned(B, 8) && ldb % 2 == 0) vec = 2;
 
-    // tile width: keep the n_cols x TW panel of B inside ~half of the L2
+    // tile width: the n_cols x TW panel of B being gathered should stay L2-resident.  Measured on B200
+    // (profiles/r1/spmm_sweep.txt): 64 columns with 16-byte loads by two half-warps is the fastest shape
+    // at Reddit scale (233 k rows: 60 MB panel) and ties with 128 at arxiv scale; 32 doubles the
+    // instruction count per gathered byte and is ~1.8x slower, so it is never chosen automatically.
     int tw = tile_cols;
-    if (tw == 0) {
-        const double budget = 56.0 * 1024 * 1024;
-        tw = 128;
-        while (tw > 32 && (double)n_cols * tw * sizeof(float) > budget) tw >>= 1;
-    }
+    if (tw == 0) tw = ((double)n_cols * 128 * sizeof(float) <= 40.0 * 1024 * 1024) ? 128 : 64;
     if (vec == 2 && tw > 64) tw = 64;
     if (vec == 1) tw = 32;
 
-    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : 256;
+    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : 512;
     // small graphs: shrink work items until the tile-0 wave covers the SMs a few times
     while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * ceil_div(k, tw) < (int64_t)sm_count() * 32) chunk >>= 1;
 

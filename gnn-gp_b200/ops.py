@@ -149,6 +149,12 @@ class CudaOps(object):
         if B.shape[0] != csr.n_cols:
             raise RuntimeError("spmm: B has %d rows, adjacency has %d columns" % (B.shape[0], csr.n_cols))
         k = B.shape[1]
+        if k >= 32 and (ldb % 4 != 0 or B.data_ptr() % 16 != 0):
+            # one streaming copy into a 16-byte-aligned, padded buffer so the gathers are 128-bit loads
+            # (e.g. the Reddit-shape feature matrix with 602 columns)
+            padded = self.empty(B.shape[0], k, B.device)
+            padded.copy_(B)
+            B, ldb = padded, self._ld(padded)
         if out is None:
             out = self.empty(csr.n_rows, k, B.device)
         self._check(out, "out", dims=2)
@@ -326,10 +332,20 @@ class CudaOps(object):
         return out
 
     # ------------------------------------------------------------------ Nystrom root pieces
+    # dtype the eigensolver runs in.  Measured on B200 (profiles/r1/accuracy_probe.json): cuSOLVER's fp32
+    # syevd/syevj through torch loses ~50x accuracy against LAPACK's ssyevd on the clamped Nystrom root
+    # (Q Q^T rel. error 6e-5 vs 1e-6 for the reference's own fp32 run); in fp64 it is 2e-7.
+    eigh_dtype = torch.float64
+
     def eigh(self, M: torch.Tensor):
-        """Symmetric eigendecomposition (ascending), cuSOLVER through torch — the one library call kept."""
+        """Symmetric eigendecomposition (ascending, lower triangle like torch's default), cuSOLVER through
+        torch — the one library call kept on the path (SURVEY.md §7 hard part 1).  Returns fp32."""
         self._check(M, "M", dims=2)
-        return torch.linalg.eigh(M if M.is_contiguous() else M.contiguous())
+        src = M if M.is_contiguous() else M.contiguous()
+        if self.eigh_dtype == torch.float32:
+            return torch.linalg.eigh(src)
+        evals, evecs = torch.linalg.eigh(src.to(self.eigh_dtype))
+        return evals.to(torch.float32), evecs.to(torch.float32)
 
     def nystrom_spectrum(self, D: torch.Tensor):
         D = self._vec(D, "D")
