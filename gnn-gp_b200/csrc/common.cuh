@@ -60,4 +60,17 @@ __device__ __forceinline__ float relu_arccos(float g, float s, float t)
     return j1 * s * t;
 }
 
+// Same expectation with the two divisions replaced by multiplications with precomputed reciprocals
+// (rs = 1/s, rt = 1/t): c moves by <= 1.5 ulp, which J1 (|dJ1/dc| <= 1/2) does not amplify; 0 * inf = NaN
+// keeps the reference's 0/0 behaviour for zero-norm rows.
+__device__ __forceinline__ float relu_arccos_rcp(float g, float rs, float rt, float s, float t)
+{
+    float c = (g * rs) * rt;
+    c = c < -1.0f ? -1.0f : (c > 1.0f ? 1.0f : c);
+    const float theta = acosf(c);
+    const float sn = sqrtf((1.0f - c) * (1.0f + c));
+    const float j1 = 0.15915494309189535f * (sn + (3.14159265358979323846f - theta) * c);
+    return j1 * s * t;
+}
+
 }  // namespace gnngp

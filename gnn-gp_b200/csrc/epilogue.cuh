@@ -33,19 +33,23 @@ struct EpiPlain {
 struct EpiArccos {
     const float *s;   // row norms  [M]
     const float *t;   // landmark norms [N]
+    const float *rs;  // 1 / s
+    const float *rt;  // 1 / t   (16-byte aligned scratch)
     float *E;
     int64_t lde;
     bool vec_ok;
     __device__ __forceinline__ void operator()(int64_t r, int64_t c, float acc) const
     {
-        E[r * lde + c] = relu_arccos(acc, __ldg(s + r), __ldg(t + c));
+        E[r * lde + c] = relu_arccos_rcp(acc, __ldg(rs + r), __ldg(rt + c), __ldg(s + r), __ldg(t + c));
     }
     __device__ __forceinline__ void vec4(int64_t r, int64_t c, float a0, float a1, float a2, float a3) const
     {
-        const float sr = __ldg(s + r);
-        const float4 tc = __ldg(reinterpret_cast<const float4 *>(t + c));   // t is 16-byte aligned, c % 4 == 0
+        const float sr = __ldg(s + r), rsr = __ldg(rs + r);
+        const float4 tc = __ldg(reinterpret_cast<const float4 *>(t + c));   // t, rt are 16-byte aligned, c % 4 == 0
+        const float4 rc = __ldg(reinterpret_cast<const float4 *>(rt + c));
         *reinterpret_cast<float4 *>(E + r * lde + c) =
-            make_float4(relu_arccos(a0, sr, tc.x), relu_arccos(a1, sr, tc.y), relu_arccos(a2, sr, tc.z), relu_arccos(a3, sr, tc.w));
+            make_float4(relu_arccos_rcp(a0, rsr, rc.x, sr, tc.x), relu_arccos_rcp(a1, rsr, rc.y, sr, tc.y),
+                        relu_arccos_rcp(a2, rsr, rc.z, sr, tc.z), relu_arccos_rcp(a3, rsr, rc.w, sr, tc.w));
     }
 };
 

@@ -45,6 +45,12 @@ __global__ void laplacian_kernel(const float *__restrict__ X, int64_t ldx, int64
     C0[i * ldc + j] = expf(-gamma * acc);
 }
 
+__global__ void reciprocal_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = 1.0f / v[i];
+}
+
 }  // namespace gnngp
 
 using namespace gnngp;
@@ -53,8 +59,9 @@ extern "C" {
 
 size_t gnngp_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K)
 {
-    if (M <= 0 || N <= 0 || K <= 0) return 256;
-    return tc::workspace_bytes(M, N, K);
+    if (M <= 0 || N <= 0 || K <= 0) return 1024;
+    // operand split of the tcgen05 engine + the reciprocal norms of the arc-cosine epilogue
+    return tc::workspace_bytes(M, N, K) + (size_t)round_up(M, 64) * 4 + (size_t)round_up(N, 64) * 4 + 512;
 }
 
 int gnngp_gemm_nt_f32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc, int64_t M,
@@ -75,8 +82,19 @@ int gnngp_gram_arccos_f32(const float *Q, int64_t ldq, int64_t n, const float *L
     GNNGP_REQUIRE(n >= 0 && n_land >= 0 && m > 0, "gram_arccos: bad sizes");
     GNNGP_REQUIRE(ldq >= m && ldl >= m && lde >= n_land, "gram_arccos: leading dimension too small");
     GNNGP_REQUIRE(n == 0 || n_land == 0 || (Q && L && s && t && E), "gram_arccos: null pointer");
-    EpiArccos epi{s, t, E, lde, aligned(E, 16) && lde % 4 == 0 && aligned(t, 16)};
-    return contract(Q, ldq, L, ldl, n, n_land, m, epi, workspace, workspace_bytes, as_stream(stream));
+    if (n == 0 || n_land == 0) return GNNGP_OK;
+    const size_t head = (size_t)round_up(n, 64) * 4 + (size_t)round_up(n_land, 64) * 4;
+    GNNGP_REQUIRE(workspace && aligned(workspace, 256) && workspace_bytes >= head + 256,
+                  "gram_arccos: workspace must be 256-byte aligned and hold gnngp_gemm_workspace_bytes(n, n_land, m)");
+    cudaStream_t st = as_stream(stream);
+    float *rs = reinterpret_cast<float *>(workspace);
+    float *rt = rs + round_up(n, 64);
+    reciprocal_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8), 256, 0, st>>>(s, n, rs);
+    GNNGP_LAUNCHED();
+    reciprocal_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_land, 256), (int64_t)sm_count() * 8), 256, 0, st>>>(t, n_land, rt);
+    GNNGP_LAUNCHED();
+    EpiArccos epi{s, t, rs, rt, E, lde, aligned(E, 16) && lde % 4 == 0 && aligned(t, 16)};
+    return contract(Q, ldq, L, ldl, n, n_land, m, epi, reinterpret_cast<char *>(workspace) + head, workspace_bytes - head, st);
 }
 
 int gnngp_initial_kernel_f32(int kind, const float *X, int64_t ldx, int64_t n, const float *R, int64_t ldr, int64_t r,

@@ -292,7 +292,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 // Measured on B200: tcgen05.mma adds into the TMEM accumulator with truncation, so a long K loop
 // accumulates a bias of ~0.5 ulp(acc) per MMA (2e-5 relative at K = 3 070, 1.7e-3 for the train Gram
 // with K = N_t = 153 k) — far above the fp32 reference.  v2 keeps each TMEM partial sum short
-// (CHUNK_KB k-blocks = 64 K-elements = 24 MMAs, starting from zero) and lets the epilogue warps add the
+// (CHUNK_KB k-blocks = 128 K-elements = 48 MMAs, starting from zero) and lets the epilogue warps add the
 // partials into a 128-column fp32 master accumulator held in REGISTERS with round-to-nearest adds.
 // Tile 128 x 128 so that one thread's master row fits the register file; four 128-column TMEM partial
 // buffers (all 512 columns) keep the MMA issuer up to four chunks ahead of the epilogue, which hides
@@ -306,7 +306,7 @@ constexpr int B_BYTES = BN * BK * 4;
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int PARTIALS = 4;                                            // 4 x 128 TMEM columns
-constexpr int CHUNK_KB = 2;                                            // k-blocks per partial sum
+constexpr int CHUNK_KB = 4;                                            // k-blocks per partial sum (128 K-elements)
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 template <class Epi>

@@ -86,6 +86,15 @@ class CudaOps(object):
     def release_workspace(self):
         self._workspace.clear()
 
+    def side_stream(self, device) -> "torch.cuda.Stream":
+        """A second stream per device, used to run the eigensolver next to the tensor-core Gram."""
+        key = ("side", device.index)
+        stream = self._workspace.get(key)
+        if stream is None:
+            stream = torch.cuda.Stream(device=device)
+            self._workspace[key] = stream
+        return stream
+
     def empty(self, n: int, m: int, device) -> torch.Tensor:
         buf = torch.empty((n, _round_up(max(m, 1), 4)), dtype=torch.float32, device=device)
         return buf[:, :m]

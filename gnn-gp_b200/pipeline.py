@@ -110,22 +110,41 @@ class Pipeline(object):
 
     def relu_nystrom(self, q: torch.Tensor, land: Landmarks) -> torch.Tensor:
         """``_ExxT_ReLU_Nystrom`` (src/compute.py:120-127): landmark Gram with the arc-cosine expectation
-        fused into its epilogue, then the Nystrom root.  The N x N_a matrix E is never materialised:
-        row blocks are streamed Gram → J1 → back-projection."""
+        fused into its epilogue, then the Nystrom root.
+
+        Schedule: the N_a x N_a landmark block is formed first and its eigendecomposition (cuSOLVER,
+        latency-bound, few SMs busy) runs on a side stream while the main stream computes E for all rows
+        on the tensor cores, row block by row block; the back-projection ``E @ (V D~)`` joins the two.
+        None of the reference's ~10 N x N_a elementwise temporaries exists; E itself is the only one."""
         ops = self.ops
         n_local, na = q.shape[0], land.count
         s = ops.row_norms(q)
         lrows = self.landmark_rows(q, land)
         t = ops.row_norms(lrows)
         emm = ops.gram_arccos(lrows, lrows, t, t)
-        w_t, v_root = self._root_factors(emm)
-        out = ops.empty(n_local, na, q.device)
-        rb = _row_block(w_t.stride(0), n_local)
-        scratch = ops.empty(rb, na, q.device)
+
+        side = ops.side_stream(q.device) if (q.is_cuda and hasattr(ops, "side_stream")) else None
+        if side is not None:
+            main = torch.cuda.current_stream(q.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                w_t, v_root = self._root_factors(emm)
+            for tensor in (emm, w_t, v_root):
+                tensor.record_stream(main)
+        else:
+            w_t, v_root = self._root_factors(emm)
+
+        e_full = ops.empty(n_local, na, q.device)
+        rb = _row_block(e_full.stride(0) if n_local > 1 else na, n_local)
         for r0 in range(0, n_local, rb):
             r1 = min(n_local, r0 + rb)
-            e_blk = ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=scratch[:r1 - r0])
-            ops.gemm_nt(e_blk, w_t, out=out[r0:r1])
+            ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=e_full[r0:r1])
+        if side is not None:
+            torch.cuda.current_stream(q.device).wait_stream(side)
+        out = ops.empty(n_local, na, q.device)
+        for r0 in range(0, n_local, rb):
+            r1 = min(n_local, r0 + rb)
+            ops.gemm_nt(e_full[r0:r1], w_t, out=out[r0:r1])
         self._put_landmark_rows(out, v_root, land)
         return out
 
