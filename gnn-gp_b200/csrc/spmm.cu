@@ -20,6 +20,8 @@
 //    the byte offset of the B row and stages {offset, value} in shared memory, from where every lane
 //    fetches it with one broadcast LDS.128; four gathers are in flight per lane before the FMAs.
 //  * columns beyond the last full tile go through the scalar, bounds-checked instantiation.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gnngp {
@@ -177,11 +179,143 @@ static int launch(const int64_t *rowptr, const int32_t *colidx, const float *val
     return GNNGP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Panel layout of the gathered operand.
+//
+// Measured (profiles/r1): with B row-major, a 64-column tile touches 256 B out of every row, i.e. one
+// strip per 4*ldb bytes across the whole matrix (2.8 GB at Reddit-shape fraction 50, 14 GB at
+// fraction 10) — the gather rate falls from 16.6 TB/s (k = 256) to 11.7 (k = 3 024) and 10.0
+// (k = 15 355) as the footprint of one tile pass outgrows the TLB reach.  Copying B once into
+// [n_tiles][n_cols][64] panels (zero-padded to a multiple of 64 columns; one streaming pass, ~1 % of
+// the SpMM) makes every tile pass gather from one contiguous 60 MB panel, turns the row offset into a
+// shift, and removes the slow scalar pass over the k % 64 tail columns.
+constexpr int PANEL = 64;
+
+__global__ void panelize_kernel(const float *__restrict__ B, int64_t ldb, int64_t n, int64_t k, int64_t n_tiles,
+                                float *__restrict__ P, bool vec_ok)
+{
+    const int64_t total = n_tiles * n * (PANEL / 4);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t q = i % (PANEL / 4);
+        const int64_t row = (i / (PANEL / 4)) % n;
+        const int64_t tile = i / ((PANEL / 4) * n);
+        const int64_t col = tile * PANEL + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *src = B + row * ldb + col;
+        if (vec_ok && col + 3 < k) {
+            v = __ldg(reinterpret_cast<const float4 *>(src));
+        } else {
+            if (col < k) v.x = __ldg(src);
+            if (col + 1 < k) v.y = __ldg(src + 1);
+            if (col + 2 < k) v.z = __ldg(src + 2);
+            if (col + 3 < k) v.w = __ldg(src + 3);
+        }
+        reinterpret_cast<float4 *>(P)[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const float *__restrict__ vals,
+                  int64_t n_rows, int64_t nnz, const float *__restrict__ P, int64_t n_cols, int64_t k, float alpha,
+                  float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks, int64_t n_tiles)
+{
+    constexpr int GROUP = kUnroll * 2;
+    __shared__ int2 staged[kWarpsPerBlock][32];          // {column id, value bits}
+    int2 *stage = staged[threadIdx.x >> 5];
+
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (item >= n_chunks * n_tiles) return;
+    const int64_t tile = item / n_chunks;
+    const int64_t piece = item - tile * n_chunks;
+    const int sub = lane >> 4;                            // two half-warps, one nonzero each per step
+    const int l16 = lane & 15;
+    const char *base = reinterpret_cast<const char *>(P + tile * n_cols * PANEL) + l16 * 16;
+    const int64_t mycol = tile * PANEL + l16 * 4;
+
+    const int64_t p0 = piece * chunk;
+    const int64_t p1 = min(p0 + chunk, nnz);
+    int64_t lo = 0, hi = n_rows - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(rowptr + mid) <= p0) lo = mid; else hi = mid - 1;
+    }
+    int64_t row = lo;
+    int64_t p = p0;
+    while (p < p1) {
+        int64_t rend = __ldg(rowptr + row + 1);
+        while (rend <= p) { ++row; rend = __ldg(rowptr + row + 1); }
+        const int64_t rstart = __ldg(rowptr + row);
+        const int64_t seg_end = min(rend, p1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t q = p; q < seg_end; q += 32) {
+            const int64_t mine = q + lane;
+            int2 entry = make_int2(0, 0);
+            if (mine < seg_end) {
+                entry.x = __ldcs(colidx + mine);
+                entry.y = __float_as_int(__ldcs(vals + mine));
+            }
+            __syncwarp();
+            stage[lane] = entry;
+            __syncwarp();
+            const int cnt = (int)min((int64_t)32, seg_end - q);
+            const int full = cnt - cnt % GROUP;
+            for (int j = 0; j < full; j += GROUP) {
+                int2 ent[kUnroll];
+                float4 b[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) ent[u] = stage[j + u * 2 + sub];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    b[u] = __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent[u].x << 8)));
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const float v = __int_as_float(ent[u].y);
+                    acc.x = fmaf(v, b[u].x, acc.x); acc.y = fmaf(v, b[u].y, acc.y);
+                    acc.z = fmaf(v, b[u].z, acc.z); acc.w = fmaf(v, b[u].w, acc.w);
+                }
+            }
+            for (int j = full + sub; j < cnt; j += 2) {
+                const int2 ent = stage[j];
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent.x << 8)));
+                const float v = __int_as_float(ent.y);
+                acc.x = fmaf(v, b.x, acc.x); acc.y = fmaf(v, b.y, acc.y);
+                acc.z = fmaf(v, b.z, acc.z); acc.w = fmaf(v, b.w, acc.w);
+            }
+        }
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+        if (sub == 0 && mycol < k) {
+            float *out = C + row * ldc + mycol;
+            const float r[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
+            const bool whole = (rstart >= p0) && (rend <= p1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (mycol + e < k) {
+                    if (whole) out[e] = r[e]; else atomicAdd(out + e, r[e]);
+                }
+            }
+        }
+        p = seg_end;
+        if (seg_end == rend) ++row;
+    }
+}
+
 }  // namespace gnngp
+
+extern "C" size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k)
+{
+    if (n_cols <= 0 || k <= 0) return 256;
+    return (size_t)gnngp::ceil_div(k, gnngp::PANEL) * gnngp::PANEL * (size_t)n_cols * sizeof(float) + 256;
+}
 
 extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows,
                                   int64_t n_cols, int64_t nnz, const float *B, int64_t ldb, int64_t k, float alpha,
-                                  float *C, int64_t ldc, int tile_cols, int nnz_per_warp, gnngp_stream_t stream)
+                                  float *C, int64_t ldc, int tile_cols, int nnz_per_warp, void *workspace,
+                                  size_t workspace_bytes, gnngp_stream_t stream)
 {
     using namespace gnngp;
     GNNGP_REQUIRE(n_rows > 0 && n_cols > 0 && nnz >= 0 && k >= 0, "spmm: bad sizes");
@@ -195,21 +329,43 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
     GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
     if (nnz == 0) return GNNGP_OK;
 
+    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : 512;
+
+    // ---- default path: gather from 64-column panels of B built in the workspace
+    if (tile_cols == 0 && workspace != nullptr && n_cols < ((int64_t)1 << 24)) {
+        const size_t need = gnngp_spmm_workspace_bytes(n_cols, k);
+        if (workspace_bytes < need) {
+            set_error("spmm: workspace %zu < %zu bytes", workspace_bytes, need);
+            return GNNGP_ERR_WORKSPACE;
+        }
+        GNNGP_REQUIRE(aligned(workspace, 256), "spmm: workspace must be 256-byte aligned");
+        const int64_t n_tiles = ceil_div(k, PANEL);
+        float *panels = reinterpret_cast<float *>(workspace);
+        const int64_t quads = n_tiles * n_cols * (PANEL / 4);
+        panelize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(quads, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
+            B, ldb, n_cols, k, n_tiles, panels, aligned(B, 16) && ldb % 4 == 0);
+        GNNGP_LAUNCHED();
+        while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * n_tiles < (int64_t)sm_count() * 32) chunk >>= 1;
+        const int64_t n_chunks = ceil_div(nnz, chunk);
+        const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
+        GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
+        spmm_panel_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k,
+                                                                        alpha, C, ldc, chunk, n_chunks, n_tiles);
+        GNNGP_LAUNCHED();
+        return GNNGP_OK;
+    }
+
+    // ---- row-major path (no workspace, or an explicit tile width): gathers straight from B
     // widest vector the gathered operand allows
     int vec = 1;
     if (aligned(B, 16) && ldb % 4 == 0) vec = 4;
     else if (aligned(B, 8) && ldb % 2 == 0) vec = 2;
 
-    // tile width: the n_cols x TW panel of B being gathered should stay L2-resident.  Measured on B200
-    // (profiles/r1/spmm_sweep.txt): 64 columns with 16-byte loads by two half-warps is the fastest shape
-    // at Reddit scale (233 k rows: 60 MB panel) and ties with 128 at arxiv scale; 32 doubles the
-    // instruction count per gathered byte and is ~1.8x slower, so it is never chosen automatically.
     int tw = tile_cols;
     if (tw == 0) tw = ((double)n_cols * 128 * sizeof(float) <= 40.0 * 1024 * 1024) ? 128 : 64;
     if (vec == 2 && tw > 64) tw = 64;
     if (vec == 1) tw = 32;
 
-    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : 512;
     // small graphs: shrink work items until the tile-0 wave covers the SMs a few times
     while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * ceil_div(k, tw) < (int64_t)sm_count() * 32) chunk >>= 1;
 

@@ -38,7 +38,7 @@ class CudaOps(object):
         self.lib = _lib.library()
         self._workspace = {}
         self._csr_cache = {}
-        self.spmm_tile_cols = 0       # 0 = automatic (see gnngp_spmm_csr_f32)
+        self.spmm_tile_cols = 0       # 0 = panel layout (default); 32/64/128 = row-major gather with that tile
         self.spmm_nnz_per_warp = 0
 
     # ------------------------------------------------------------------ plumbing
@@ -158,20 +158,19 @@ class CudaOps(object):
         if B.shape[0] != csr.n_cols:
             raise RuntimeError("spmm: B has %d rows, adjacency has %d columns" % (B.shape[0], csr.n_cols))
         k = B.shape[1]
-        if k >= 32 and (ldb % 4 != 0 or B.data_ptr() % 16 != 0):
-            # one streaming copy into a 16-byte-aligned, padded buffer so the gathers are 128-bit loads
-            # (e.g. the Reddit-shape feature matrix with 602 columns)
-            padded = self.empty(B.shape[0], k, B.device)
-            padded.copy_(B)
-            B, ldb = padded, self._ld(padded)
         if out is None:
             out = self.empty(csr.n_rows, k, B.device)
         self._check(out, "out", dims=2)
         if out.shape != (csr.n_rows, k) or (k > 1 and out.stride(1) != 1):
             raise RuntimeError("spmm: out must be a [%d x %d] row-major view" % (csr.n_rows, k))
+        wptr, need = None, 0
+        if int(self.spmm_tile_cols) == 0:          # default: gather from 64-column panels built in a workspace
+            need = self.lib.query("gnngp_spmm_workspace_bytes", csr.n_cols, k)
+            ws = self.workspace(need + 256, B.device, "spmm")
+            wptr = (ws.data_ptr() + 255) // 256 * 256
         self.lib.call("gnngp_spmm_csr_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(),
                       csr.n_rows, csr.n_cols, csr.nnz, B.data_ptr(), ldb, k, float(alpha), out.data_ptr(),
-                      self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), self._stream())
+                      self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), wptr, need, self._stream())
         return out
 
     # ------------------------------------------------------------------ dense contractions

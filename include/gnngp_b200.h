@@ -59,13 +59,16 @@ int gnngp_csr_from_coo(const int64_t *row, const int64_t *col, const float *val,
 /* ---- K1: CSR SpMM  C[:, 0:k] = alpha * A @ B ----------------------------------------------
  * Replaces `sigma_w * A @ Q` (src/compute.py:142,145,164,169,186,205,209) and `A @ (A @ C0).T`
  * (src/compute.py:132,135,151,156,176,195,198).  B: [n_cols x k] ld ldb, C: [n_rows x k] ld ldc.
- * tile_cols: width of the column tile kept L2-resident (0 = choose from n_cols; else 32/64/128).
- * nnz_per_warp: nonzeros per warp work item (0 = default).  Rows that straddle a work item are
+ * Default (tile_cols = 0 and a workspace of gnngp_spmm_workspace_bytes(n_cols, k)): B is copied once
+ * into 64-column panels in the workspace and gathered from there.  tile_cols = 32/64/128 (or a null
+ * workspace) gathers straight from the row-major B with that tile width.
+ * nnz_per_warp: nonzeros per warp work item (0 = default 512).  Rows that straddle a work item are
  * combined with fp32 atomics, so C is zero-filled first (the call does that itself). */
+size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k);
 int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals,
                        int64_t n_rows, int64_t n_cols, int64_t nnz, const float *B, int64_t ldb,
                        int64_t k, float alpha, float *C, int64_t ldc, int tile_cols, int nnz_per_warp,
-                       gnngp_stream_t stream);
+                       void *workspace, size_t workspace_bytes, gnngp_stream_t stream);
 
 /* ---- dense contractions  D = A * B^T  (A: [M x K] ld lda, B: [N x K] ld ldb) ----------------
  * Both operands K-contiguous ("NT").  The 3xTF32 engine needs a workspace for the hi/lo operand
