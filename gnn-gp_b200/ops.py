@@ -152,6 +152,20 @@ class CudaOps(object):
     def clear_cache(self) -> None:
         self._csr_cache.clear()
 
+    def restrict_columns(self, csr: CsrMatrix, cols: torch.Tensor) -> CsrMatrix:
+        """CSR of ``A[:, cols]`` with column ids renumbered to positions in ``cols`` (one pass over the
+        nonzeros with torch index ops; done once per landmark set)."""
+        dev = csr.colidx.device
+        lookup = torch.full((csr.n_cols,), -1, dtype=torch.int32, device=dev)
+        lookup[cols] = torch.arange(cols.numel(), dtype=torch.int32, device=dev)
+        renum = lookup[csr.colidx.long()]
+        keep = renum >= 0
+        running = torch.zeros(csr.nnz + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(keep, 0, out=running[1:])
+        rowptr = running[csr.rowptr].contiguous()
+        return CsrMatrix(rowptr, renum[keep].contiguous(), csr.vals[keep].contiguous(), csr.n_rows, int(cols.numel()),
+                         csr.row_offset)
+
     # ------------------------------------------------------------------ K1 SpMM
     def spmm(self, csr: CsrMatrix, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, ldb = self._mat(B, "B")

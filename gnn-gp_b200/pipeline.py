@@ -53,6 +53,15 @@ class RowLayout(object):
 class Landmarks(object):
     def __init__(self, mask: torch.Tensor, layout: RowLayout):
         self.local_rows, self.local_pos, self.count = layout.local_index(mask)
+        self.global_idx = torch.nonzero(mask, as_tuple=False).flatten().contiguous()
+        self._restricted = None
+
+    def restricted(self, csr, ops):
+        """This rank's adjacency rows restricted to the landmark columns (column ids = landmark order);
+        built once per landmark set and reused by every layer."""
+        if self._restricted is None or self._restricted[0] is not csr:
+            self._restricted = (csr, ops.restrict_columns(csr, self.global_idx))
+        return self._restricted[1]
 
 
 def _row_block(na_ld: int, n_local: int) -> int:
@@ -148,6 +157,52 @@ class Pipeline(object):
         self._put_landmark_rows(out, v_root, land)
         return out
 
+    def relu_nystrom_propagate(self, q: torch.Tensor, land: Landmarks, csr, alpha: float, out: torch.Tensor) -> torch.Tensor:
+        """``out = alpha * A @ Ny(g(Q Qᵀ))`` — the pair (src/compute.py:144-145) of a GCN / GCN2 layer,
+        re-associated so that the eigendecomposition leaves the critical path.
+
+        With W = V D~ and R = V sqrt(D+) (src/compute.py:12-16) the factor is E W on every row except the
+        landmark rows, which are R: ``Ny = E W + P (R - E_mm W)`` (P scatters landmark rows).  Hence
+        ``A Ny = (A E) W + A[:, landmarks] (R - E_mm W)``: the large sparse product ``A E`` needs no
+        eigen-information and runs on the main stream while cuSOLVER works on the side stream; afterwards
+        one tensor-core contraction applies W and a sparse product over the landmark columns only
+        (~N_a/N of the nonzeros) adds the correction.  Same flops as the reference order, and the
+        all-gather of the sharded mode moves E instead of E W (same size)."""
+        ops = self.ops
+        n_local, na = q.shape[0], land.count
+        s = ops.row_norms(q)
+        lrows = self.landmark_rows(q, land)
+        t = ops.row_norms(lrows)
+        emm = ops.gram_arccos(lrows, lrows, t, t)
+
+        side = ops.side_stream(q.device) if (q.is_cuda and hasattr(ops, "side_stream")) else None
+        if side is not None:
+            main = torch.cuda.current_stream(q.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                w_t, v_root = self._root_factors(emm)
+            for tensor in (emm, w_t, v_root):
+                tensor.record_stream(main)
+        else:
+            w_t, v_root = self._root_factors(emm)
+
+        e_full = ops.empty(n_local, na, q.device)
+        rb = _row_block(e_full.stride(0) if n_local > 1 else na, n_local)
+        for r0 in range(0, n_local, rb):
+            r1 = min(n_local, r0 + rb)
+            ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=e_full[r0:r1])
+        ae = self.propagate(csr, e_full, 1.0)                        # A E: independent of the eigensolver
+        del e_full
+        if side is not None:
+            torch.cuda.current_stream(q.device).wait_stream(side)
+        delta = ops.gemm_nt(emm, w_t)                                # E_mm W
+        ops.affine(delta, v_root, delta, 1.0, -1.0, 0.0)             # R - E_mm W  (zero where nothing is clamped)
+        ops.spmm(land.restricted(csr, ops), delta, alpha, out=out)   # alpha * A[:, landmarks] (R - E_mm W)
+        for r0 in range(0, n_local, rb):
+            r1 = min(n_local, r0 + rb)
+            ops.gemm_nt(ae[r0:r1], w_t, alpha=alpha, out=out[r0:r1], beta=1.0)
+        return out
+
     def propagate(self, csr, block: torch.Tensor, alpha: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``alpha * A @ X`` for this rank's rows of A: all-gather X's row blocks, then the CSR SpMM."""
         full = self.comm.all_gather_rows(block, self._layout(block.shape[0]))
@@ -223,8 +278,7 @@ class Pipeline(object):
             self.propagate(csr, q0, sigma_w, out=q[:, :ni])
             ops.fill_col(q, na, sigma_b)
             for _ in range(layers - 1):
-                e = self.relu_nystrom(q, land)
-                self.propagate(csr, e, sigma_w, out=q[:, :na])
+                self.relu_nystrom_propagate(q, land, csr, sigma_w, out=q[:, :na])
                 ops.fill_col(q, na, sigma_b)
             return q
         if method == "GIN":
@@ -248,14 +302,12 @@ class Pipeline(object):
         if method == "GCN2":
             alpha = params.get("alpha", 0.1)
             theta = params.get("theta", 0.5)
-            e = self.relu_nystrom(q0, land)
             q = ops.zeros(n, na + ni, dev)
-            self.propagate(csr, e, sigma_w, out=q[:, :na])
+            self.relu_nystrom_propagate(q0, land, csr, sigma_w, out=q[:, :na])
             for j in range(layers - 1):
-                e = self.relu_nystrom(q, land)
                 beta = math.log(theta / (j + 1) + 1)
                 coef = math.sqrt((sigma_w * beta) ** 2 + (1 - beta) ** 2)
-                self.propagate(csr, e, (1 - alpha) * coef, out=q[:, :na])
+                self.relu_nystrom_propagate(q, land, csr, (1 - alpha) * coef, out=q[:, :na])
                 ops.affine(q[:, na:na + ni], q0, None, alpha * coef, 0.0, 0.0)
             return q
         raise Exception("Unsupported layer type!")

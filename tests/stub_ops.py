@@ -39,6 +39,10 @@ class StubOps(object):
         idx = A._indices()
         return self.csr_from_coo(idx[0], idx[1], A._values(), A.shape[0], A.shape[1])
 
+    def restrict_columns(self, csr, cols):
+        dense_cols = csr.mat.index_select(1, cols).coalesce()
+        return _Csr(dense_cols, csr.n_rows, int(cols.numel()), csr.row_offset)
+
     def spmm(self, csr, B, alpha=1.0, out=None):
         res = alpha * torch.sparse.mm(csr.mat, B.contiguous())
         if out is None:
