@@ -75,6 +75,22 @@ int gnngp_gemm_nt_f32(const float *A, int64_t lda, const float *B, int64_t ldb, 
     return contract(A, lda, B, ldb, M, N, K, epi, workspace, workspace_bytes, as_stream(stream));
 }
 
+int gnngp_syrk_f32(const float *A, int64_t lda, float *C, int64_t ldc, int64_t n, int64_t K, void *workspace,
+                   size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(n >= 0 && K >= 0 && lda >= K && ldc >= n, "syrk: bad sizes");
+    GNNGP_REQUIRE(n == 0 || (A && C), "syrk: null pointer");
+    if (n == 0) return GNNGP_OK;
+    cudaStream_t st = as_stream(stream);
+    EpiPlain epi{C, ldc, 1.0f, 0.0f, aligned(C, 16) && ldc % 4 == 0};
+    if (use_tensor_cores(n, n, K) && g_gemm_engine.load() != 3) {
+        // the operand is split once and used on both sides; tiles above the diagonal are skipped (their
+        // entries keep whatever C held: callers zero C, the eigensolver only reads the lower triangle)
+        return tc::gemm_nt_tc(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st, true, true);
+    }
+    return contract(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st);
+}
+
 int gnngp_gram_arccos_f32(const float *Q, int64_t ldq, int64_t n, const float *L, int64_t ldl, int64_t n_land,
                           int64_t m, const float *s, const float *t, float *E, int64_t lde, void *workspace,
                           size_t workspace_bytes, gnngp_stream_t stream)

@@ -309,7 +309,19 @@ constexpr int PARTIALS = 4;                                            // 4 x 12
 constexpr int CHUNK_KB = 4;                                            // k-blocks per partial sum (128 K-elements)
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-template <class Epi>
+// lower-triangular tile enumeration for symmetric products (A == B): t -> (i, j), j <= i, row by row
+__device__ __forceinline__ TileCoord raster_lower(int64_t t)
+{
+    int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    TileCoord c;
+    c.m_blk = i;
+    c.n_blk = t - i * (i + 1) / 2;
+    return c;
+}
+
+template <class Epi, bool LOWER>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -340,7 +352,7 @@ gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t total = tiles_m * tiles_n;
+    const int64_t total = LOWER ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
     const int chunks = (k_blocks + CHUNK_KB - 1) / CHUNK_KB;
 
     if (warp == 0) {
@@ -349,7 +361,7 @@ gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord tc_ = raster(tile, tiles_m, tiles_n);
+                const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
                 const int32_t m0 = (int32_t)(tc_.m_blk * BM), n0 = (int32_t)(tc_.n_blk * BN);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -406,7 +418,7 @@ gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         int part = 0;
         uint32_t part_phase = 0;
         for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const TileCoord tc_ = raster(tile, tiles_m, tiles_n);
+            const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
             float master[BN];
 #pragma unroll
             for (int j = 0; j < BN; ++j) master[j] = 0.0f;
@@ -526,7 +538,8 @@ inline size_t workspace_bytes(int64_t M, int64_t N, int64_t K)
 
 template <class Epi>
 static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                      const Epi &epi, void *workspace, size_t ws_bytes, cudaStream_t st, bool chunked = true)
+                      const Epi &epi, void *workspace, size_t ws_bytes, cudaStream_t st, bool chunked = true,
+                      bool lower = false)
 {
     if (M <= 0 || N <= 0) return GNNGP_OK;
     GNNGP_REQUIRE(K > 0, "tcgen05 gemm: K must be positive");
@@ -560,8 +573,21 @@ static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, 
 
     if (chunked) {
         const int64_t tiles_m = ceil_div(M, v2::BM), tiles_n = ceil_div(N, v2::BN);
+        if (lower) {      // symmetric product: only tiles on or below the diagonal are computed
+            GNNGP_REQUIRE(M == N, "tcgen05 gemm: the lower-triangle mode needs a square result");
+            const int grid = (int)std::min<int64_t>(tiles_m * (tiles_m + 1) / 2, sm_count());
+            auto kernel_l = v2::gemm_nt_tc2_kernel<Epi, true>;
+            static bool configured_l = false;
+            if (!configured_l) {
+                GNNGP_CUDA(cudaFuncSetAttribute(kernel_l, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+                configured_l = true;
+            }
+            kernel_l<<<grid, THREADS, v2::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
+            GNNGP_LAUNCHED();
+            return GNNGP_OK;
+        }
         const int grid = (int)std::min<int64_t>(tiles_m * tiles_n, sm_count());
-        auto kernel2 = v2::gemm_nt_tc2_kernel<Epi>;
+        auto kernel2 = v2::gemm_nt_tc2_kernel<Epi, false>;
         static bool configured2 = false;
         if (!configured2) {
             GNNGP_CUDA(cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));

@@ -215,13 +215,15 @@ __global__ void panelize_kernel(const float *__restrict__ B, int64_t ldb, int64_
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+constexpr int kPanelUnroll = 8;      // gathers in flight per lane (two half-warps -> 16 nonzeros per step)
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const float *__restrict__ vals,
                   int64_t n_rows, int64_t nnz, const float *__restrict__ P, int64_t n_cols, int64_t k, float alpha,
                   float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks, int64_t n_tiles)
 {
-    constexpr int GROUP = kUnroll * 2;
-    __shared__ int2 staged[kWarpsPerBlock][32];          // {column id, value bits}
+    constexpr int GROUP = kPanelUnroll * 2;
+    __shared__ int2 staged[kWarpsPerBlock][32];          // {column id, value bits} of the current batch
     int2 *stage = staged[threadIdx.x >> 5];
 
     const int lane = threadIdx.x & 31;
@@ -229,7 +231,7 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
     if (item >= n_chunks * n_tiles) return;
     const int64_t tile = item / n_chunks;
     const int64_t piece = item - tile * n_chunks;
-    const int sub = lane >> 4;                            // two half-warps, one nonzero each per step
+    const int sub = lane >> 4;                            // two half-warps, one nonzero each per gather
     const int l16 = lane & 15;
     const char *base = reinterpret_cast<const char *>(P + tile * n_cols * PANEL) + l16 * 16;
     const int64_t mycol = tile * PANEL + l16 * 4;
@@ -242,6 +244,24 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
         if (__ldg(rowptr + mid) <= p0) lo = mid; else hi = mid - 1;
     }
     int64_t row = lo;
+
+    // The (colidx, vals) stream of the work item is consumed in batches of 32 that do not depend on row
+    // boundaries; the batch after the current one is already in registers (software prefetch), so the
+    // HBM latency of the adjacency stream overlaps the gathers of the current batch.
+    auto fetch = [&](int64_t at) {
+        int2 e = make_int2(0, 0);
+        const int64_t mine = at + lane;
+        if (mine < p1) {
+            e.x = __ldcs(colidx + mine);
+            e.y = __float_as_int(__ldcs(vals + mine));
+        }
+        return e;
+    };
+    int64_t batch = p0;                                   // first nonzero of the staged batch
+    int2 ahead = fetch(p0 + 32);
+    stage[lane] = fetch(p0);
+    __syncwarp();
+
     int64_t p = p0;
     while (p < p1) {
         int64_t rend = __ldg(rowptr + row + 1);
@@ -249,40 +269,53 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
         const int64_t rstart = __ldg(rowptr + row);
         const int64_t seg_end = min(rend, p1);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t q = p; q < seg_end; q += 32) {
-            const int64_t mine = q + lane;
-            int2 entry = make_int2(0, 0);
-            if (mine < seg_end) {
-                entry.x = __ldcs(colidx + mine);
-                entry.y = __float_as_int(__ldcs(vals + mine));
+        while (p < seg_end) {
+            if (p >= batch + 32) {                        // advance the staged batch
+                batch += 32;
+                __syncwarp();
+                stage[lane] = ahead;
+                __syncwarp();
+                ahead = fetch(batch + 32);
             }
-            __syncwarp();
-            stage[lane] = entry;
-            __syncwarp();
-            const int cnt = (int)min((int64_t)32, seg_end - q);
-            const int full = cnt - cnt % GROUP;
-            for (int j = 0; j < full; j += GROUP) {
-                int2 ent[kUnroll];
-                float4 b[kUnroll];
+            const int first = (int)(p - batch);
+            const int last = (int)min((int64_t)32, seg_end - batch);
+            const int full = first + (last - first) / GROUP * GROUP;
+            for (int j = first; j < full; j += GROUP) {
+                int2 ent[kPanelUnroll];
+                float4 b[kPanelUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) ent[u] = stage[j + u * 2 + sub];
+                for (int u = 0; u < kPanelUnroll; ++u) ent[u] = stage[j + u * 2 + sub];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
+                for (int u = 0; u < kPanelUnroll; ++u)
                     b[u] = __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent[u].x << 8)));
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
+                for (int u = 0; u < kPanelUnroll; ++u) {
                     const float v = __int_as_float(ent[u].y);
                     acc.x = fmaf(v, b[u].x, acc.x); acc.y = fmaf(v, b[u].y, acc.y);
                     acc.z = fmaf(v, b[u].z, acc.z); acc.w = fmaf(v, b[u].w, acc.w);
                 }
             }
-            for (int j = full + sub; j < cnt; j += 2) {
-                const int2 ent = stage[j];
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent.x << 8)));
-                const float v = __int_as_float(ent.y);
-                acc.x = fmaf(v, b.x, acc.x); acc.y = fmaf(v, b.y, acc.y);
-                acc.z = fmaf(v, b.z, acc.z); acc.w = fmaf(v, b.w, acc.w);
+            // ragged remainder (< 16 nonzeros): all loads first, then the FMAs
+            {
+                int2 ent[kPanelUnroll];
+                float4 b[kPanelUnroll];
+#pragma unroll
+                for (int u = 0; u < kPanelUnroll; ++u) {
+                    const int j = full + u * 2 + sub;
+                    ent[u] = (j < last) ? stage[j] : make_int2(-1, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < kPanelUnroll; ++u)
+                    b[u] = (ent[u].x >= 0) ? __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent[u].x << 8)))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < kPanelUnroll; ++u) {
+                    const float v = __int_as_float(ent[u].y);
+                    acc.x = fmaf(v, b[u].x, acc.x); acc.y = fmaf(v, b[u].y, acc.y);
+                    acc.z = fmaf(v, b[u].z, acc.z); acc.w = fmaf(v, b[u].w, acc.w);
+                }
             }
+            p = batch + last;
         }
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
@@ -299,7 +332,6 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
                 }
             }
         }
-        p = seg_end;
         if (seg_end == rend) ++row;
     }
 }

@@ -212,6 +212,15 @@ class CudaOps(object):
                       M, N, K, float(alpha), float(beta), ws, nbytes, self._stream())
         return out
 
+    def syrk(self, A: torch.Tensor) -> torch.Tensor:
+        """A @ A.T with only the lower triangle guaranteed (upper entries are zero or mirrored)."""
+        A, lda = self._mat(A, "A")
+        n, K = A.shape
+        out = self.zeros(n, n, A.device)
+        ws, nbytes = self._gemm_ws(n, n, K, A.device)
+        self.lib.call("gnngp_syrk_f32", A.data_ptr(), lda, out.data_ptr(), self._ld(out), n, K, ws, nbytes, self._stream())
+        return out
+
     def gram_arccos(self, Q: torch.Tensor, L: torch.Tensor, s: torch.Tensor, t: torch.Tensor,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """E = J1-arccos((Q L^T) / s / t^T) * s * t^T — reference ``_ExxT_ReLU_Nystrom`` before the root."""

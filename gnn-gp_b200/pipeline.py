@@ -391,7 +391,7 @@ class Pipeline(object):
         ops, comm = self.ops, self.comm
         n_total = q.shape[0] if n_total is None else n_total
         qb_t = ops.gather_rows_t(q, train_rows)                       # [m x n_t]
-        gram = ops.gemm_nt(qb_t, qb_t)                                # Q_b^T Q_b
+        gram = ops.syrk(qb_t)                                         # Q_b^T Q_b (lower triangle; eigh reads only that)
         y_t, trailing = self._targets_t(y, train_rows, num_classes)
         qty_t = ops.gemm_nt(y_t, qb_t)                                # (Q_b^T y_b)^T  [C x m]
         sumsq = ops.row_norms(q, sqrt=False)

@@ -11,7 +11,7 @@ from typing import Dict, List
 
 import torch
 
-TIMED = ("csr_from_coo", "spmm", "gemm_nt", "gram_arccos", "initial_kernel", "nugget_coeff", "nugget_sweep", "row_norms",
+TIMED = ("csr_from_coo", "spmm", "gemm_nt", "syrk", "restrict_columns", "gram_arccos", "initial_kernel", "nugget_coeff", "nugget_sweep", "row_norms",
          "gather_rows", "scatter_rows", "gather_rows_t", "gather_cols", "affine", "eigh", "nystrom_spectrum",
          "scale_cols", "arccos_dense", "onehot_t", "argmax_count", "sqerr_sum", "mean", "fill_col")
 
@@ -41,6 +41,8 @@ class OpTimer(object):
                 info = (int(args[0].shape[0]), int(args[1].shape[0]), int(args[0].shape[1]))
             elif name == "nugget_sweep":
                 info = (int(args[0].shape[0]), int(args[1].shape[0]), int(args[0].shape[1]))
+            elif name == "syrk":
+                info = (int(args[0].shape[0]), int(args[0].shape[0]), int(args[0].shape[1]))
             elif name == "eigh":
                 info = (int(args[0].shape[0]),)
             self.records.append((name, info, start, stop))

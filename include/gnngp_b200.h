@@ -40,8 +40,9 @@ int gnngp_abi_version(void);
 const char *gnngp_last_error(void);
 /* SM count and compute capability of the current device (host out-pointers). */
 int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor);
-/* Dense-contraction engine: 0 = fp32 CUDA-core tiles, 1 = tcgen05 3xTF32 (TMA + TMEM), 2 = auto
- * (tcgen05 when the shape fills a 128x256 tile grid).  Returns the previous setting. */
+/* Dense-contraction engine: 0 = fp32 CUDA-core tiles, 1 = tcgen05 3xTF32 with chunked accumulation
+ * (TMA + TMEM), 2 = auto (tcgen05 when the shape fills the 128x128 tile grid), 3 = the unchunked 128x256
+ * tcgen05 kernel (biased accumulation; measurement only).  Returns the previous setting. */
 int gnngp_set_gemm_engine(int engine);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gnngp_launch_count(void);
@@ -81,6 +82,12 @@ size_t gnngp_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gnngp_gemm_nt_f32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                       int64_t M, int64_t N, int64_t K, float alpha, float beta,
                       void *workspace, size_t workspace_bytes, gnngp_stream_t stream);
+
+/* K5: symmetric product C = A A^T (A: [n x K]); only the tiles on or below the diagonal are guaranteed to
+ * be written (zero C first).  Replaces `Q[mb].T @ Q[mb]` (src/predict.py:57), whose only consumer is
+ * torch.linalg.eigh (lower triangle). */
+int gnngp_syrk_f32(const float *A, int64_t lda, float *C, int64_t ldc, int64_t n, int64_t K, void *workspace,
+                   size_t workspace_bytes, gnngp_stream_t stream);
 
 /* K2: landmark Gram with the ReLU arc-cosine expectation fused into the epilogue.
  * E[i,j] = J1(clamp((Q_i . L_j) / s_i / t_j)) * s_i * t_j,  J1(c) = (sin th + (pi - th) cos th)/(2 pi),

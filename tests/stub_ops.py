@@ -57,6 +57,9 @@ class StubOps(object):
         out.copy_(res if beta == 0.0 else res + beta * out)
         return out
 
+    def syrk(self, A):
+        return torch.tril(A @ A.T)          # like the CUDA operator: only the lower triangle is meaningful
+
     def gram_arccos(self, Q, L, s, t, out=None):
         c = torch.clamp(Q @ L.T / s.view(-1, 1) / t.view(1, -1), -1, 1)
         theta = torch.arccos(c)

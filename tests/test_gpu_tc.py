@@ -67,3 +67,15 @@ def test_tc_engine_end_to_end_case(ops):
     data, masks, nugget = cases.build_inputs(case)
     out, _ = run_public_api(case, data, masks, nugget)
     runner.check_against_golden(name, out, masks)
+
+
+def test_tc_syrk_lower_triangle(ops):
+    g = torch.Generator().manual_seed(21)
+    a = torch.randn(1500, 4000, generator=g)
+    got = ops.syrk(a.cuda()).cpu().double()
+    want = a.double() @ a.double().T
+    low = torch.tril(torch.ones(1500, 1500, dtype=torch.bool))
+    assert float((got[low] - want[low]).norm() / want[low].norm()) < 2e-6
+    w1, _ = torch.linalg.eigh(got)             # eigh reads the lower triangle only
+    w2, _ = torch.linalg.eigh(want)
+    assert float((w1 - w2).abs().max() / w2.abs().max()) < 1e-6

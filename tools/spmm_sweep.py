@@ -27,7 +27,7 @@ def timeit(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 
 
-for shape, ks in (("reddit", (602, 1024)), ("arxiv", (128, 2048))):
+for shape, ks in (("reddit", (602, 1024, 3024)), ("arxiv", (128, 2048))):
     data = synth.make_graph(shape, seed=0, device=dev)
     n = data.num_nodes
     csr = ops.csr_from_coo(data.edge_index[0], data.edge_index[1], data.edge_attr, n, n)
@@ -36,13 +36,18 @@ for shape, ks in (("reddit", (602, 1024)), ("arxiv", (128, 2048))):
     for k in ks:
         b = torch.randn(n, (k + 3) // 4 * 4, device=dev)[:, :k]
         c = ops.empty(n, k, dev)
-        for tile in (32, 64, 128):
-            for chunk in (64, 128, 256, 512, 1024):
+        for tile in (64, 128):
+            for chunk in (256, 512):
                 ops.spmm_tile_cols, ops.spmm_nnz_per_warp = tile, chunk
                 ms = timeit(lambda: ops.spmm(csr, b, 1.0, out=c))
                 gather_tbs = 4.0 * csr.nnz * k / (ms * 1e-3) / 1e12
                 out["%s k=%d tile=%d chunk=%d" % (shape, k, tile, chunk)] = ms
                 print("%s k=%4d tile=%3d chunk=%4d  %8.3f ms  gather %.2f TB/s" % (shape, k, tile, chunk, ms, gather_tbs), flush=True)
+        for chunk in (128, 256, 512, 1024, 2048):
+            ops.spmm_tile_cols, ops.spmm_nnz_per_warp = 0, chunk
+            ms = timeit(lambda: ops.spmm(csr, b, 1.0, out=c))
+            out["%s k=%d panel chunk=%d" % (shape, k, chunk)] = ms
+            print("%s k=%4d PANEL    chunk=%4d  %8.3f ms  gather %.2f TB/s" % (shape, k, chunk, ms, 4.0 * csr.nnz * k / (ms * 1e-3) / 1e12), flush=True)
         ops.spmm_tile_cols, ops.spmm_nnz_per_warp = 0, 0
         # cuSPARSE through torch, for context only (the reference's GPU path)
         a = torch.sparse_coo_tensor(data.edge_index, data.edge_attr, (n, n)).coalesce()
