@@ -361,7 +361,8 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
     GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
     if (nnz == 0) return GNNGP_OK;
 
-    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : 512;
+    // work-item size: 1024 nonzeros on large graphs (Reddit shape: 108 ms vs 112 ms at 512), 512 otherwise
+    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : (nnz >= ((int64_t)1 << 25) ? 1024 : 512);
 
     // ---- default path: gather from 64-column panels of B built in the workspace
     if (tile_cols == 0 && workspace != nullptr && n_cols < ((int64_t)1 << 24)) {

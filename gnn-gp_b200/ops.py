@@ -91,7 +91,9 @@ class CudaOps(object):
         key = ("side", device.index)
         stream = self._workspace.get(key)
         if stream is None:
-            stream = torch.cuda.Stream(device=device)
+            # highest priority: the eigensolver's many small kernels must not queue behind the grid-filling
+            # SpMM / tensor-core kernels of the main stream they are meant to overlap with
+            stream = torch.cuda.Stream(device=device, priority=-1)
             self._workspace[key] = stream
         return stream
 
@@ -178,10 +180,19 @@ class CudaOps(object):
         if out.shape != (csr.n_rows, k) or (k > 1 and out.stride(1) != 1):
             raise RuntimeError("spmm: out must be a [%d x %d] row-major view" % (csr.n_rows, k))
         wptr, need = None, 0
-        if int(self.spmm_tile_cols) == 0:          # default: gather from 64-column panels built in a workspace
+        # Measured on B200 (profiles/r1/call7_spmm_sweep.txt): the 64-column panel copy pays off for dense rows
+        # and wide / misaligned operands (Reddit shape: 108 vs 121 ms at k=3024, 22 vs 26 ms at k=602); for
+        # short rows (arxiv shape, 15 nonzeros per row) gathering straight from the row-major operand wins.
+        use_panels = int(self.spmm_tile_cols) == 0 and csr.nnz >= 64 * csr.n_rows and k >= 256
+        if use_panels:
             need = self.lib.query("gnngp_spmm_workspace_bytes", csr.n_cols, k)
             ws = self.workspace(need + 256, B.device, "spmm")
             wptr = (ws.data_ptr() + 255) // 256 * 256
+        elif k >= 32 and (ldb % 4 != 0 or B.data_ptr() % 16 != 0):
+            # row-major gather: one streaming copy into a 16-byte-aligned, padded buffer so the gathers are 128-bit
+            padded = self.empty(B.shape[0], k, B.device)
+            padded.copy_(B)
+            B, ldb = padded, self._ld(padded)
         self.lib.call("gnngp_spmm_csr_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(),
                       csr.n_rows, csr.n_cols, csr.nnz, B.data_ptr(), ldb, k, float(alpha), out.data_ptr(),
                       self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), wptr, need, self._stream())

@@ -63,7 +63,7 @@ int gnngp_csr_from_coo(const int64_t *row, const int64_t *col, const float *val,
  * Default (tile_cols = 0 and a workspace of gnngp_spmm_workspace_bytes(n_cols, k)): B is copied once
  * into 64-column panels in the workspace and gathered from there.  tile_cols = 32/64/128 (or a null
  * workspace) gathers straight from the row-major B with that tile width.
- * nnz_per_warp: nonzeros per warp work item (0 = default 512).  Rows that straddle a work item are
+ * nnz_per_warp: nonzeros per warp work item (0 = default: 512, or 1024 on graphs with >= 2^25 nonzeros).  Rows that straddle a work item are
  * combined with fp32 atomics, so C is zero-filled first (the call does that itself). */
 size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k);
 int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals,
