@@ -270,11 +270,13 @@ def run_ours(args):
     timer.enabled = True
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" selects exactly this region
     ev0.record()
     for _ in range(args.steps):
         summary = step()
     ev1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     elapsed = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device=dev)
     if world > 1:
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
