@@ -103,6 +103,32 @@ class Pipeline(object):
         v_root = ops.scale_cols(evecs, root)                   # V * sqrt(D+): the landmark rows of the factor
         return w_t, v_root
 
+    def _mark(self, ref: torch.Tensor):
+        """Event on the current stream (None off-GPU)."""
+        if not ref.is_cuda or not hasattr(self.ops, "side_stream"):
+            return None
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(ref.device))
+        return event
+
+    def _side_root(self, kmm: torch.Tensor, ready):
+        """``_root_factors`` on the high-priority side stream, ordered after ``ready``; the main stream
+        waits for it on return.  ``torch.linalg.eigh`` blocks the HOST until its status word is back, so
+        callers enqueue every main-stream kernel that does not need the factors BEFORE calling this: those
+        kernels then execute while cuSOLVER (latency-bound, few SMs) works."""
+        if ready is None:
+            return self._root_factors(kmm)
+        dev = kmm.device
+        main, side = torch.cuda.current_stream(dev), self.ops.side_stream(dev)
+        side.wait_event(ready)
+        kmm.record_stream(side)
+        with torch.cuda.stream(side):
+            w_t, v_root = self._root_factors(kmm)
+        main.wait_stream(side)
+        w_t.record_stream(main)
+        v_root.record_stream(main)
+        return w_t, v_root
+
     def _put_landmark_rows(self, out: torch.Tensor, v_root: torch.Tensor, land: Landmarks) -> None:
         ops = self.ops
         rows = v_root if self.comm.world == 1 else ops.gather_rows(v_root, land.local_pos)
@@ -132,24 +158,13 @@ class Pipeline(object):
         t = ops.row_norms(lrows)
         emm = ops.gram_arccos(lrows, lrows, t, t)
 
-        side = ops.side_stream(q.device) if (q.is_cuda and hasattr(ops, "side_stream")) else None
-        if side is not None:
-            main = torch.cuda.current_stream(q.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                w_t, v_root = self._root_factors(emm)
-            for tensor in (emm, w_t, v_root):
-                tensor.record_stream(main)
-        else:
-            w_t, v_root = self._root_factors(emm)
-
         e_full = ops.empty(n_local, na, q.device)
         rb = _row_block(e_full.stride(0) if n_local > 1 else na, n_local)
-        for r0 in range(0, n_local, rb):
+        ready = self._mark(q)                                        # emm is complete at this point of the main stream
+        for r0 in range(0, n_local, rb):                             # enqueued BEFORE the eigensolver call (see _side_root)
             r1 = min(n_local, r0 + rb)
             ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=e_full[r0:r1])
-        if side is not None:
-            torch.cuda.current_stream(q.device).wait_stream(side)
+        w_t, v_root = self._side_root(emm, ready)
         out = ops.empty(n_local, na, q.device)
         for r0 in range(0, n_local, rb):
             r1 = min(n_local, r0 + rb)
@@ -175,26 +190,15 @@ class Pipeline(object):
         t = ops.row_norms(lrows)
         emm = ops.gram_arccos(lrows, lrows, t, t)
 
-        side = ops.side_stream(q.device) if (q.is_cuda and hasattr(ops, "side_stream")) else None
-        if side is not None:
-            main = torch.cuda.current_stream(q.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                w_t, v_root = self._root_factors(emm)
-            for tensor in (emm, w_t, v_root):
-                tensor.record_stream(main)
-        else:
-            w_t, v_root = self._root_factors(emm)
-
         e_full = ops.empty(n_local, na, q.device)
         rb = _row_block(e_full.stride(0) if n_local > 1 else na, n_local)
+        ready = self._mark(q)                                        # emm is complete at this point of the main stream
         for r0 in range(0, n_local, rb):
             r1 = min(n_local, r0 + rb)
             ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=e_full[r0:r1])
         ae = self.propagate(csr, e_full, 1.0)                        # A E: independent of the eigensolver
         del e_full
-        if side is not None:
-            torch.cuda.current_stream(q.device).wait_stream(side)
+        w_t, v_root = self._side_root(emm, ready)                    # eigh runs while the kernels above execute
         delta = ops.gemm_nt(emm, w_t)                                # E_mm W
         ops.affine(delta, v_root, delta, 1.0, -1.0, 0.0)             # R - E_mm W  (zero where nothing is clamped)
         ops.spmm(land.restricted(csr, ops), delta, alpha, out=out)   # alpha * A[:, landmarks] (R - E_mm W)
