@@ -29,6 +29,19 @@ struct EpiPlain {
     }
 };
 
+// C += alpha * acc, atomically (split-K partial products into a zeroed C)
+struct EpiAtomicAdd {
+    float *C;
+    int64_t ldc;
+    float alpha;
+    static constexpr bool vec_ok = false;
+    __device__ __forceinline__ void operator()(int64_t r, int64_t c, float acc) const { atomicAdd(C + r * ldc + c, alpha * acc); }
+    __device__ __forceinline__ void vec4(int64_t r, int64_t c, float a0, float a1, float a2, float a3) const
+    {
+        (*this)(r, c, a0); (*this)(r, c + 1, a1); (*this)(r, c + 2, a2); (*this)(r, c + 3, a3);
+    }
+};
+
 // K2: ReLU arc-cosine expectation on the landmark Gram (src/compute.py:124-126)
 struct EpiArccos {
     const float *s;   // row norms  [M]

@@ -71,8 +71,17 @@ int gnngp_gemm_nt_f32(const float *A, int64_t lda, const float *B, int64_t ldb, 
     GNNGP_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm_nt: negative size");
     GNNGP_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm_nt: leading dimension too small");
     GNNGP_REQUIRE(M == 0 || N == 0 || (A && B && C), "gemm_nt: null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (!use_tensor_cores(M, N, K) && beta == 0.0f && M > 0 && N > 0) {
+        const int splits = simt_split_k(M, N, K);
+        if (splits > 1) {          // skinny product with a long K: split K over blockIdx.z, accumulate atomically
+            GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+            EpiAtomicAdd epi{C, ldc, alpha};
+            return gemm_nt_simt_splitk(A, lda, B, ldb, M, N, K, splits, epi, st);
+        }
+    }
     EpiPlain epi{C, ldc, alpha, beta, aligned(C, 16) && ldc % 4 == 0};
-    return contract(A, lda, B, ldb, M, N, K, epi, workspace, workspace_bytes, as_stream(stream));
+    return contract(A, lda, B, ldb, M, N, K, epi, workspace, workspace_bytes, st);
 }
 
 int gnngp_syrk_f32(const float *A, int64_t lda, float *C, int64_t ldc, int64_t n, int64_t K, void *workspace,

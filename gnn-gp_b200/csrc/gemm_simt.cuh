@@ -5,6 +5,8 @@
 // 3xTF32 engine.  128 x 128 x 16 block tile, 8 x 8 register tile per thread, global->register
 // prefetch of the next K-slab while the current one is consumed from shared memory.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gnngp {
@@ -30,11 +32,21 @@ __device__ __forceinline__ float4 load_k4(const float *__restrict__ base, int64_
     return v;
 }
 
+// blockIdx.z selects a K-range of `k_span` elements (split-K for skinny products with a long K, e.g. the
+// [C x m x N_t] projection Q_b^T y_b of the fit: 1 x 24 tiles but K = 153 k); with gridDim.z > 1 the epilogue
+// functor must accumulate atomically into a zeroed output (EpiAtomicAdd).
 template <class Epi>
 __global__ void __launch_bounds__(256)
 gemm_nt_simt_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb, int64_t M,
-                    int64_t N, int64_t K, bool vec_a, bool vec_b, Epi epi)
+                    int64_t N, int64_t K_total, int64_t k_span, bool vec_a, bool vec_b, Epi epi)
 {
+    {   // restrict this block to its K-range; everything below uses (A, B, K) of the range
+        const int64_t k_begin = (int64_t)blockIdx.z * k_span;
+        A += k_begin;
+        B += k_begin;
+        // the vector path needs the shifted base to stay 16-byte aligned: k_span is a multiple of 16
+    }
+    const int64_t K = min(k_span, K_total - (int64_t)blockIdx.z * k_span);
     __shared__ float As[SIMT_BK][SIMT_BM + SIMT_PAD];
     __shared__ float Bs[SIMT_BK][SIMT_BN + SIMT_PAD];
 
@@ -113,7 +125,32 @@ static int gemm_nt_simt(const float *A, int64_t lda, const float *B, int64_t ldb
     GNNGP_REQUIRE(gy <= 65535, "gemm: N = %lld needs more than 65535 column tiles", (long long)N);
     const bool vec_a = aligned(A, 16) && lda % 4 == 0;
     const bool vec_b = aligned(B, 16) && ldb % 4 == 0;
-    gemm_nt_simt_kernel<Epi><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(A, lda, B, ldb, M, N, K, vec_a, vec_b, epi);
+    const int64_t span = std::max<int64_t>(K, 1);
+    gemm_nt_simt_kernel<Epi><<<dim3((unsigned)gx, (unsigned)gy, 1), 256, 0, st>>>(A, lda, B, ldb, M, N, K, span, vec_a, vec_b, epi);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+
+// number of K-splits worth using for an [M x N x K] product on the CUDA-core tiles (1 = do not split)
+inline int simt_split_k(int64_t M, int64_t N, int64_t K)
+{
+    const int64_t tiles = ceil_div(M, SIMT_BM) * ceil_div(N, SIMT_BN);
+    const int64_t want = (int64_t)sm_count() * 4;
+    if (tiles >= want / 2 || K < 4096) return 1;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div(want, tiles), ceil_div(K, 1024)), 65535));
+}
+
+template <class Epi>
+static int gemm_nt_simt_splitk(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                               int splits, const Epi &epi, cudaStream_t st)
+{
+    const int64_t gx = ceil_div(M, SIMT_BM), gy = ceil_div(N, SIMT_BN);
+    GNNGP_REQUIRE(gy <= 65535, "gemm: N = %lld needs more than 65535 column tiles", (long long)N);
+    const int64_t span = round_up(ceil_div(K, splits), 16);
+    const int64_t gz = ceil_div(K, span);
+    const bool vec_a = aligned(A, 16) && lda % 4 == 0;
+    const bool vec_b = aligned(B, 16) && ldb % 4 == 0;
+    gemm_nt_simt_kernel<Epi><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, st>>>(A, lda, B, ldb, M, N, K, span, vec_a, vec_b, epi);
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }

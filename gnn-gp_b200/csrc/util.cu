@@ -257,6 +257,51 @@ __global__ void argmax_count_kernel(const float *__restrict__ fitted, const int6
     if (threadIdx.x < 8 && local[threadIdx.x]) atomicAdd(counts + g * 8 + threadIdx.x, local[threadIdx.x]);
 }
 
+// Tiled variant for small class counts: a block stages 256 nodes x C values (contiguous in memory) with
+// coalesced 16-byte loads, then every thread scans its own node from shared memory (stride C words: for odd
+// C no bank conflicts).  One pass over fitted at close to HBM speed instead of one 164-byte read per warp.
+__global__ void __launch_bounds__(256)
+argmax_count_tiled_kernel(const float *__restrict__ fitted, const int64_t *__restrict__ y, const uint8_t *__restrict__ member,
+                          int64_t n, int C, int32_t *__restrict__ counts)
+{
+    extern __shared__ float tile[];
+    __shared__ int32_t local[8];
+    const int64_t g = blockIdx.y;
+    const int64_t node0 = (int64_t)blockIdx.x * 256;
+    const int nodes = (int)min((int64_t)256, n - node0);
+    if (threadIdx.x < 8) local[threadIdx.x] = 0;
+    const float *src = fitted + (g * n + node0) * C;
+    const int total = nodes * C;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int quads = total >> 2;
+        for (int i = threadIdx.x; i < quads; i += 256)
+            reinterpret_cast<float4 *>(tile)[i] = __ldcs(reinterpret_cast<const float4 *>(src) + i);
+        for (int i = (quads << 2) + threadIdx.x; i < total; i += 256) tile[i] = __ldcs(src + i);
+    } else {
+        for (int i = threadIdx.x; i < total; i += 256) tile[i] = __ldcs(src + i);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nodes) {
+        const uint8_t bits = __ldg(member + node0 + threadIdx.x);
+        if (bits) {
+            const float *p = tile + threadIdx.x * C;
+            float best = -INFINITY;
+            int arg = 0x7fffffff;
+            for (int c = 0; c < C; ++c) {
+                const float v = p[c];
+                if (beats(v, c, best, arg)) { best = v; arg = c; }
+            }
+            if ((int64_t)arg == __ldg(y + node0 + threadIdx.x)) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (bits & (1u << s)) atomicAdd(&local[s], 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && local[threadIdx.x]) atomicAdd(counts + g * 8 + threadIdx.x, local[threadIdx.x]);
+}
+
 __global__ void sqerr_sum_kernel(const float *__restrict__ fitted, const float *__restrict__ y,
                                  const uint8_t *__restrict__ member, int64_t G, int64_t n, int64_t k, double *__restrict__ sse)
 {
@@ -439,6 +484,17 @@ int gnngp_argmax_count(const float *fitted, const int64_t *y, const uint8_t *mem
     GNNGP_REQUIRE(G > 0 && G <= 65535 && n > 0 && C > 0 && fitted && y && membership && counts, "argmax_count: bad arguments");
     cudaStream_t st = as_stream(stream);
     GNNGP_CUDA(cudaMemsetAsync(counts, 0, (size_t)G * 8 * sizeof(int32_t), st));
+    if (C <= 96) {
+        static bool configured = false;
+        if (!configured) {
+            GNNGP_CUDA(cudaFuncSetAttribute(argmax_count_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 * 4));
+            configured = true;
+        }
+        argmax_count_tiled_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)G), 256, (size_t)256 * C * sizeof(float), st>>>(
+            fitted, y, membership, n, (int)C, counts);
+        GNNGP_LAUNCHED();
+        return GNNGP_OK;
+    }
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 4));
     argmax_count_kernel<<<dim3(gx, (unsigned)G), 256, 0, st>>>(fitted, y, membership, G, n, C, counts);
     GNNGP_LAUNCHED();

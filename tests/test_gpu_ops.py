@@ -232,3 +232,29 @@ def test_cpu_tensors_are_rejected(ops):
         ops.row_norms(torch.randn(4, 4))
     with pytest.raises(RuntimeError):
         ops.gemm_nt(torch.randn(4, 4).cuda(), torch.randn(4, 5).cuda())
+
+
+def test_gemm_nt_split_k_for_skinny_long_k(ops):
+    """[41 x 3000 x 150k]-like products (Q_b^T y_b of the fit) go through the split-K path."""
+    g = torch.Generator().manual_seed(77)
+    a, b = torch.randn(41, 60000, generator=g), torch.randn(515, 60000, generator=g)
+    got = ops.gemm_nt(a.cuda(), b.cuda(), alpha=1.5)
+    assert rel(got, 1.5 * (a.double() @ b.double().T)) < 2e-6
+    out = torch.full((41, 520), 3.0).cuda()
+    ops.gemm_nt(a.cuda(), b.cuda(), out=out[:, 2:517])
+    assert rel(out[:, 2:517], a.double() @ b.double().T) < 2e-6
+    assert bool((out[:, :2] == 3.0).all()) and bool((out[:, 517:] == 3.0).all())
+
+
+@pytest.mark.parametrize("n,C,G", [(1000, 41, 5), (257, 3, 2), (300, 120, 3)])
+def test_argmax_count_variants(ops, ref, n, C, G):
+    g = torch.Generator().manual_seed(n + C)
+    f = torch.randn(G, n, C, generator=g)
+    f[0, 3, :] = 1.25                      # all tied -> index 0
+    f[G - 1, n - 1, C - 1] = float("nan")  # NaN wins
+    y = torch.randint(0, C, (n,), generator=g)
+    y[3] = 0
+    y[n - 1] = C - 1
+    member = torch.randint(0, 16, (n,), generator=g).to(torch.uint8)
+    got = ops.argmax_count(f.cuda(), y.cuda(), member.cuda()).cpu()
+    assert torch.equal(got, ref.argmax_count(f, y, member))
