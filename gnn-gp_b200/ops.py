@@ -10,6 +10,7 @@ multiple of 4 floats, so that the SpMM can gather them with 128-bit loads.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -86,8 +87,11 @@ class CudaOps(object):
     def release_workspace(self):
         self._workspace.clear()
 
-    def side_stream(self, device) -> "torch.cuda.Stream":
-        """A second stream per device, used to run the eigensolver next to the tensor-core Gram."""
+    def side_stream(self, device):
+        """A second stream per device, used to run the eigensolver next to the sparse product / Gram
+        (None when GNNGP_NO_OVERLAP=1: everything on one stream, for A/B measurements)."""
+        if os.environ.get("GNNGP_NO_OVERLAP") == "1":
+            return None
         key = ("side", device.index)
         stream = self._workspace.get(key)
         if stream is None:

@@ -105,7 +105,7 @@ class Pipeline(object):
 
     def _mark(self, ref: torch.Tensor):
         """Event on the current stream (None off-GPU)."""
-        if not ref.is_cuda or not hasattr(self.ops, "side_stream"):
+        if not ref.is_cuda or not hasattr(self.ops, "side_stream") or self.ops.side_stream(ref.device) is None:
             return None
         event = torch.cuda.Event()
         event.record(torch.cuda.current_stream(ref.device))
