@@ -88,9 +88,12 @@ class CudaOps(object):
         self._workspace.clear()
 
     def side_stream(self, device):
-        """A second stream per device, used to run the eigensolver next to the sparse product / Gram
-        (None when GNNGP_NO_OVERLAP=1: everything on one stream, for A/B measurements)."""
-        if os.environ.get("GNNGP_NO_OVERLAP") == "1":
+        """A second, high-priority stream per device for running the eigensolver next to the sparse product,
+        or None (the default).  Measured on B200 (profiles/r1/call11_overlap_ab.txt): cuSOLVER's
+        tridiagonalisation kernels fill the grid and are L2-bound like the SpMM, so concurrent execution
+        stretches both and the step time does not improve (0.339 s single stream vs 0.343 s overlapped at
+        fraction 50; 6.83 vs 6.86 s at fraction 10).  GNNGP_OVERLAP=1 turns the overlapped schedule on."""
+        if os.environ.get("GNNGP_OVERLAP") != "1":
             return None
         key = ("side", device.index)
         stream = self._workspace.get(key)

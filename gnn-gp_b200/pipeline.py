@@ -147,10 +147,9 @@ class Pipeline(object):
         """``_ExxT_ReLU_Nystrom`` (src/compute.py:120-127): landmark Gram with the arc-cosine expectation
         fused into its epilogue, then the Nystrom root.
 
-        Schedule: the N_a x N_a landmark block is formed first and its eigendecomposition (cuSOLVER,
-        latency-bound, few SMs busy) runs on a side stream while the main stream computes E for all rows
-        on the tensor cores, row block by row block; the back-projection ``E @ (V D~)`` joins the two.
-        None of the reference's ~10 N x N_a elementwise temporaries exists; E itself is the only one."""
+        The N_a x N_a landmark block is formed and eigendecomposed first; then row blocks of Q are streamed
+        through Gram -> J1 epilogue -> back-projection ``E @ (V D~)`` on the tensor cores.  None of the
+        reference's ~10 N x N_a elementwise temporaries exists, and E itself only as a <= 1 GiB block."""
         ops = self.ops
         n_local, na = q.shape[0], land.count
         s = ops.row_norms(q)
@@ -158,17 +157,28 @@ class Pipeline(object):
         t = ops.row_norms(lrows)
         emm = ops.gram_arccos(lrows, lrows, t, t)
 
-        e_full = ops.empty(n_local, na, q.device)
-        rb = _row_block(e_full.stride(0) if n_local > 1 else na, n_local)
         ready = self._mark(q)                                        # emm is complete at this point of the main stream
-        for r0 in range(0, n_local, rb):                             # enqueued BEFORE the eigensolver call (see _side_root)
-            r1 = min(n_local, r0 + rb)
-            ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=e_full[r0:r1])
-        w_t, v_root = self._side_root(emm, ready)
         out = ops.empty(n_local, na, q.device)
-        for r0 in range(0, n_local, rb):
-            r1 = min(n_local, r0 + rb)
-            ops.gemm_nt(e_full[r0:r1], w_t, out=out[r0:r1])
+        rb = _row_block(out.stride(0) if n_local > 1 else na, n_local)
+        if ready is None:
+            # single stream (default): E is never materialised — row blocks are streamed
+            # Gram -> J1 epilogue -> back-projection through a <= 1 GiB scratch block
+            w_t, v_root = self._root_factors(emm)
+            scratch = ops.empty(min(rb, n_local), na, q.device)
+            for r0 in range(0, n_local, rb):
+                r1 = min(n_local, r0 + rb)
+                e_blk = ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=scratch[:r1 - r0])
+                ops.gemm_nt(e_blk, w_t, out=out[r0:r1])
+        else:
+            # overlapped schedule: E for all rows is enqueued BEFORE the host-blocking eigensolver call
+            e_full = ops.empty(n_local, na, q.device)
+            for r0 in range(0, n_local, rb):
+                r1 = min(n_local, r0 + rb)
+                ops.gram_arccos(q[r0:r1], lrows, s[r0:r1], t, out=e_full[r0:r1])
+            w_t, v_root = self._side_root(emm, ready)
+            for r0 in range(0, n_local, rb):
+                r1 = min(n_local, r0 + rb)
+                ops.gemm_nt(e_full[r0:r1], w_t, out=out[r0:r1])
         self._put_landmark_rows(out, v_root, land)
         return out
 
@@ -206,6 +216,15 @@ class Pipeline(object):
             r1 = min(n_local, r0 + rb)
             ops.gemm_nt(ae[r0:r1], w_t, alpha=alpha, out=out[r0:r1], beta=1.0)
         return out
+
+    def _layer(self, q: torch.Tensor, land: Landmarks, csr, alpha: float, out: torch.Tensor) -> torch.Tensor:
+        """``out = alpha * A @ Ny(g(Q Qᵀ))``: the reference order (root, then propagate) by default, the
+        re-associated overlapped schedule when the operator set offers a side stream (GNNGP_OVERLAP=1)."""
+        overlapped = getattr(self, "force_reassociated", False) or (
+            q.is_cuda and hasattr(self.ops, "side_stream") and self.ops.side_stream(q.device) is not None)
+        if overlapped:
+            return self.relu_nystrom_propagate(q, land, csr, alpha, out)
+        return self.propagate(csr, self.relu_nystrom(q, land), alpha, out=out)
 
     def propagate(self, csr, block: torch.Tensor, alpha: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``alpha * A @ X`` for this rank's rows of A: all-gather X's row blocks, then the CSR SpMM."""
@@ -282,7 +301,7 @@ class Pipeline(object):
             self.propagate(csr, q0, sigma_w, out=q[:, :ni])
             ops.fill_col(q, na, sigma_b)
             for _ in range(layers - 1):
-                self.relu_nystrom_propagate(q, land, csr, sigma_w, out=q[:, :na])
+                self._layer(q, land, csr, sigma_w, q[:, :na])
                 ops.fill_col(q, na, sigma_b)
             return q
         if method == "GIN":
@@ -307,11 +326,11 @@ class Pipeline(object):
             alpha = params.get("alpha", 0.1)
             theta = params.get("theta", 0.5)
             q = ops.zeros(n, na + ni, dev)
-            self.relu_nystrom_propagate(q0, land, csr, sigma_w, out=q[:, :na])
+            self._layer(q0, land, csr, sigma_w, q[:, :na])
             for j in range(layers - 1):
                 beta = math.log(theta / (j + 1) + 1)
                 coef = math.sqrt((sigma_w * beta) ** 2 + (1 - beta) ** 2)
-                self.relu_nystrom_propagate(q, land, csr, (1 - alpha) * coef, out=q[:, :na])
+                self._layer(q, land, csr, (1 - alpha) * coef, q[:, :na])
                 ops.affine(q[:, na:na + ni], q0, None, alpha * coef, 0.0, 0.0)
             return q
         raise Exception("Unsupported layer type!")

@@ -27,3 +27,14 @@ def test_row_block_streaming_is_exact(monkeypatch):
     monkeypatch.setattr(pl, "_row_block", lambda na_ld, n_local: 37)
     got = runner.run_pipeline(StubOps(), case, data, masks, nugget)["Q"]
     assert torch.allclose(ref @ ref.T, got @ got.T, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny-GCN-nys2-L3", "tiny-GCN2-nys2-L3", "tinyreg-GCN2-nys1-L3", "small-GCN-nys4-L2"])
+def test_reassociated_layer_schedule_matches_reference(name, monkeypatch):
+    """A Ny(E) = (A E) W + A[:, landmarks] (R - E_mm W): the schedule used when the eigensolver is overlapped."""
+    import gnngp_b200.pipeline as pl
+    monkeypatch.setattr(pl.Pipeline, "force_reassociated", True, raising=False)
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    out = runner.run_pipeline(StubOps(), case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
