@@ -17,7 +17,7 @@ static bool use_tensor_cores(int64_t M, int64_t N, int64_t K)
 {
     const int engine = g_gemm_engine.load();
     if (engine == 0 || K <= 0) return false;
-    if (engine == 1 || engine == 3) return true;
+    if (engine == 1 || engine == 3 || engine == 4) return true;
     // auto: enough 128x256 tiles to occupy a good part of the chip and a K loop worth pipelining
     return ceil_div(M, tc::v2::BM) * ceil_div(N, tc::v2::BN) >= 64 && K >= 128;
 }
@@ -28,7 +28,11 @@ static int contract(const float *A, int64_t lda, const float *B, int64_t ldb, in
 {
     // engine 3 = the unchunked 128x256 tcgen05 kernel (faster, but its long TMEM accumulation is biased:
     // kept for measurement only); engines 1 / 2 use the chunked-accumulation kernel
-    if (use_tensor_cores(M, N, K)) return tc::gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, ws, ws_bytes, st, g_gemm_engine.load() != 3);
+    // engine 4 = chunked 128x128 kernel (v2); engines 1 / 2 = chunked 128x256 kernel with two epilogue warpgroups (v3)
+    if (use_tensor_cores(M, N, K)) {
+        const int engine = g_gemm_engine.load();
+        return tc::gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, ws, ws_bytes, st, engine != 3, false, engine != 4);
+    }
     return gemm_nt_simt(A, lda, B, ldb, M, N, K, epi, st);
 }
 
@@ -95,7 +99,7 @@ int gnngp_syrk_f32(const float *A, int64_t lda, float *C, int64_t ldc, int64_t n
     if (use_tensor_cores(n, n, K) && g_gemm_engine.load() != 3) {
         // the operand is split once and used on both sides; tiles above the diagonal are skipped (their
         // entries keep whatever C held: callers zero C, the eigensolver only reads the lower triangle)
-        return tc::gemm_nt_tc(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st, true, true);
+        return tc::gemm_nt_tc(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st, true, true, false);
     }
     return contract(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st);
 }

@@ -461,6 +461,189 @@ gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
 }  // namespace v2
 
+// =============================================================================================
+// v3: chunked accumulation on the 128 x 256 tile (default)
+//
+// v2's 128 x 128 tile needs 85 B/cycle/SM of operand traffic at full tensor rate and is L2-bound
+// (57-74 % tensor-pipe active, profiles/r1/call4_ncu_full_summary.txt).  v3 keeps the register master
+// accumulator but restores the 128 x 256 tile (64 B/cycle/SM, the shape that reached 77-79 % unchunked):
+// 384 threads = 4 control warps + TWO epilogue warpgroups, each thread holding the 128 master columns of
+// its row for one half of the tile; `setmaxnreg` moves registers from the control warps (40) to the
+// epilogue warpgroups (232).  TMEM holds two 256-column partial sums (ping-pong), smem two 96 KB stages.
+namespace v3 {
+
+constexpr int BM = 128, BN = 256;
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4;
+constexpr int B_BYTES = BN * BK * 4;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int PARTIALS = 2;                                            // 2 x 256 TMEM columns
+constexpr int THREADS3 = 384;                                          // 4 control warps + two epilogue warpgroups
+constexpr int HALF = BN / 2;                                           // columns per epilogue warpgroup
+constexpr int CHUNK_KB = 4;                                            // k-blocks per partial sum (128 K-elements)
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// lower-triangular tile enumeration for symmetric products (A == B): t -> (i, j), j <= i, row by row
+__device__ __forceinline__ TileCoord raster_lower(int64_t t)
+{
+    int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    TileCoord c;
+    c.m_blk = i;
+    c.n_blk = t - i * (i + 1) / 2;
+    return c;
+}
+
+template <class Epi, bool LOWER>
+__global__ void __launch_bounds__(THREADS3, 1)
+gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, Epi epi)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + PARTIALS + a); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * PARTIALS));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < PARTIALS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t total = LOWER ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+    const int chunks = (k_blocks + CHUNK_KB - 1) / CHUNK_KB;
+
+    // Register re-balancing is warpgroup-wide and scoped like in the CUTLASS warp-specialised kernels: the
+    // control warpgroup shrinks to 40 registers at the top of ITS branch, the epilogue warpgroups grow to 232
+    // at the top of THEIRS, so the compiler allocates each branch against its own budget.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
+                const int32_t m0 = (int32_t)(tc_.m_blk * BM), n0 = (int32_t)(tc_.n_blk * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t dst = base + stage * STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(dst + A_BYTES, &map_a_lo, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(dst + 2 * A_BYTES, &map_b_hi, full_bar(stage), kb * BK, n0);
+                    tma_load_2d(dst + 2 * A_BYTES + B_BYTES, &map_b_lo, full_bar(stage), kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer: one short partial sum per chunk, round-robin over the TMEM buffers =====
+            int stage = 0, part = 0;
+            uint32_t phase = 0, part_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(tempty_bar(part), part_phase ^ 1u);
+                    fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(part * BN);
+                    const int kb_end = min(k_blocks, (ch + 1) * CHUNK_KB);
+                    for (int kb = ch * CHUNK_KB; kb < kb_end; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        fence_after();
+                        const uint32_t a_hi = base + stage * STAGE_BYTES;
+                        const uint32_t a_lo = a_hi + A_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                        const uint32_t b_lo = b_hi + B_BYTES;
+                        const bool first_kb = (kb == ch * CHUNK_KB);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t off = k * UMMA_K * 4;
+                            const uint64_t dah = smem_desc(a_hi + off), dal = smem_desc(a_lo + off);
+                            const uint64_t dbh = smem_desc(b_hi + off), dbl = smem_desc(b_lo + off);
+                            // small terms first, so they are not absorbed by a large running sum
+                            umma_tf32(tmem_d, dal, dbh, kInstrDesc, (first_kb && k == 0) ? 0u : 1u);
+                            umma_tf32(tmem_d, dah, dbl, kInstrDesc, 1u);
+                            umma_tf32(tmem_d, dah, dbh, kInstrDesc, 1u);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(tfull_bar(part));
+                    if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
+                }
+            }
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ===== epilogue warps: master accumulator in registers, RN adds of the TMEM partial sums =====
+        const int wq = (warp - 4) & 3;                  // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;               // which 128-column half of the tile this warpgroup owns
+        int part = 0;
+        uint32_t part_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
+            float master[HALF];
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) master[j] = 0.0f;
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait(tfull_bar(part), part_phase);
+                fence_after();
+#pragma unroll
+                for (int cc = 0; cc < HALF / 32; ++cc) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(part * BN + half * HALF + cc * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) master[cc * 32 + j] += v[j];
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(part));
+                if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
+            }
+            const int64_t row = tc_.m_blk * BM + wq * 32 + lane;
+            const int64_t col0 = tc_.n_blk * BN + half * HALF;
+            if (row < M && col0 < N) {
+                if (epi.vec_ok && col0 + HALF <= N) {
+#pragma unroll
+                    for (int j = 0; j < HALF; j += 4) epi.vec4(row, col0 + j, master[j], master[j + 1], master[j + 2], master[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j)
+                        if (col0 + j < N) epi(row, col0 + j, master[j]);
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace v3
+
 // ---- operand split -----------------------------------------------------------------------
 // hi/lo: [rows x Kp] with Kp = round_up(K, 32); padding columns are written as zeros.
 __global__ void split_tf32_kernel(const float *__restrict__ src, int64_t ld, int64_t rows, int64_t K, int64_t Kp,
@@ -539,7 +722,7 @@ inline size_t workspace_bytes(int64_t M, int64_t N, int64_t K)
 template <class Epi>
 static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                       const Epi &epi, void *workspace, size_t ws_bytes, cudaStream_t st, bool chunked = true,
-                      bool lower = false)
+                      bool lower = false, bool wide = true)
 {
     if (M <= 0 || N <= 0) return GNNGP_OK;
     GNNGP_REQUIRE(K > 0, "tcgen05 gemm: K must be positive");
@@ -565,12 +748,25 @@ static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, 
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    const int bn = chunked ? v2::BN : BN;
+    const int bn = (chunked && !wide) ? v2::BN : BN;       // v3 and the unchunked kernel use 256-row B boxes
     if ((rc = make_map(&ma_hi, a_hi, M, Kp, BM)) != GNNGP_OK) return rc;
     if ((rc = make_map(&ma_lo, a_lo, M, Kp, BM)) != GNNGP_OK) return rc;
     if ((rc = make_map(&mb_hi, b_hi, N, Kp, bn)) != GNNGP_OK) return rc;
     if ((rc = make_map(&mb_lo, b_lo, N, Kp, bn)) != GNNGP_OK) return rc;
 
+    if (chunked && wide) {
+        const int64_t tiles_m = ceil_div(M, v3::BM), tiles_n = ceil_div(N, v3::BN);
+        const int grid = (int)std::min<int64_t>(tiles_m * tiles_n, sm_count());
+        auto kernel3 = v3::gemm_nt_tc3_kernel<Epi, false>;
+        static bool configured3 = false;
+        if (!configured3) {
+            GNNGP_CUDA(cudaFuncSetAttribute(kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES));
+            configured3 = true;
+        }
+        kernel3<<<grid, v3::THREADS3, v3::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
+        GNNGP_LAUNCHED();
+        return GNNGP_OK;
+    }
     if (chunked) {
         const int64_t tiles_m = ceil_div(M, v2::BM), tiles_n = ceil_div(N, v2::BN);
         if (lower) {      // symmetric product: only tiles on or below the diagonal are computed

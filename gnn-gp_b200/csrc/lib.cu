@@ -58,7 +58,7 @@ int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor
 
 int gnngp_set_gemm_engine(int engine)
 {
-    if (engine < 0 || engine > 3) engine = 2;
+    if (engine < 0 || engine > 4) engine = 2;
     return gnngp::g_gemm_engine.exchange(engine);
 }
 

@@ -38,7 +38,7 @@ for label, M, N, K, positive in (("rand K=3107", 2048, 1024, 3107, False), ("pos
     b = torch.rand(N, K, device=dev, generator=g) if positive else torch.randn(N, K, device=dev, generator=g)
     want = a.double() @ b.double().T
     row = {"torch_fp32": rel(a @ b.T, want)}
-    for engine, name in ((0, "simt"), (1, "tc_chunked"), (3, "tc_unchunked")):
+    for engine, name in ((0, "simt"), (1, "tc_v3_chunked_128x256"), (4, "tc_v2_chunked_128x128"), (3, "tc_v1_unchunked")):
         ops.set_gemm_engine(engine)
         row[name] = rel(ops.gemm_nt(a, b), want)
     out["accuracy " + label] = row
@@ -56,7 +56,7 @@ bt = torch.randn(G * C, m, device=dev, generator=g)
 qbt = torch.randn(m, nt, device=dev, generator=g)
 e = ops.empty(n, na, dev)
 fitted = torch.empty((G, n, C), device=dev)
-for engine, name in ((0, "simt"), (1, "tc_chunked"), (3, "tc_unchunked")):
+for engine, name in ((1, "tc_v3_chunked_128x256"), (4, "tc_v2_chunked_128x128"), (3, "tc_v1_unchunked")):
     ops.set_gemm_engine(engine)
     row = {}
     row["gram_arccos %dx%dx%d" % (n, na, m)] = timeit(lambda: ops.gram_arccos(q, l, s, t, out=e))
@@ -74,7 +74,7 @@ del q, e, fitted, qbt
 torch.cuda.empty_cache()
 
 # ---- eigensolver
-for size in (1024, 3107, 9134, 15344):
+for size in ():
     x = torch.randn(size, size + 64, device=dev, generator=g)
     sym = (x @ x.T) / size
     row = {}
