@@ -215,6 +215,35 @@ __global__ void panelize_kernel(const float *__restrict__ B, int64_t ldb, int64_
     }
 }
 
+// Fused all-gather + layout transform for the row-sharded mode: every rank pulls the row blocks of the
+// operand straight out of its peers' memory (NVLink P2P loads through pointers exchanged with torch
+// symmetric memory) and writes them into its local 64-column panels — one kernel instead of an NCCL
+// all-gather into a staging buffer followed by the panel copy.  peer[r] is rank r's [rows_per_rank x ld] block.
+__global__ void panelize_peers_kernel(const float *const *__restrict__ peer, int64_t rows_per_rank, int64_t ld, int64_t n,
+                                      int64_t k, int64_t n_tiles, float *__restrict__ P)
+{
+    const int64_t total = n_tiles * n * (PANEL / 4);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t q = i % (PANEL / 4);
+        const int64_t row = (i / (PANEL / 4)) % n;
+        const int64_t tile = i / ((PANEL / 4) * n);
+        const int64_t col = tile * PANEL + q * 4;
+        const int64_t owner = row / rows_per_rank;
+        const float *src = peer[owner] + (row - owner * rows_per_rank) * ld + col;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + 3 < k) {                       // ld % 4 == 0 and 16-byte aligned blocks are required by the caller
+            v = *reinterpret_cast<const float4 *>(src);
+        } else {
+            if (col < k) v.x = src[0];
+            if (col + 1 < k) v.y = src[1];
+            if (col + 2 < k) v.z = src[2];
+            if (col + 3 < k) v.w = src[3];
+        }
+        reinterpret_cast<float4 *>(P)[i] = v;
+    }
+}
+
 constexpr int kPanelUnroll = 8;      // gathers in flight per lane (two half-warps -> 16 nonzeros per step)
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
@@ -342,6 +371,44 @@ extern "C" size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k)
 {
     if (n_cols <= 0 || k <= 0) return 256;
     return (size_t)gnngp::ceil_div(k, gnngp::PANEL) * gnngp::PANEL * (size_t)n_cols * sizeof(float) + 256;
+}
+
+extern "C" int gnngp_panelize_peers_f32(const void *peer_ptrs_dev, int world, int64_t rows_per_rank, int64_t ld, int64_t n,
+                                        int64_t k, float *panels, gnngp_stream_t stream)
+{
+    using namespace gnngp;
+    GNNGP_REQUIRE(peer_ptrs_dev && panels && world > 0 && rows_per_rank > 0 && n > 0 && k > 0, "panelize_peers: bad arguments");
+    GNNGP_REQUIRE(ld % 4 == 0 && ld >= k, "panelize_peers: ld must be a multiple of 4 and >= k");
+    GNNGP_REQUIRE((int64_t)world * rows_per_rank >= n, "panelize_peers: world * rows_per_rank < n");
+    const int64_t n_tiles = ceil_div(k, PANEL);
+    const int64_t quads = n_tiles * n * (PANEL / 4);
+    panelize_peers_kernel<<<(unsigned)std::min<int64_t>(ceil_div(quads, 256), (int64_t)sm_count() * 16), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float *const *>(peer_ptrs_dev), rows_per_rank, ld, n, k, n_tiles, panels);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+
+extern "C" int gnngp_spmm_panels_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows,
+                                     int64_t n_cols, int64_t nnz, const float *panels, int64_t k, float alpha, float *C,
+                                     int64_t ldc, int nnz_per_warp, gnngp_stream_t stream)
+{
+    using namespace gnngp;
+    GNNGP_REQUIRE(n_rows > 0 && n_cols > 0 && nnz >= 0 && k > 0 && ldc >= k, "spmm_panels: bad sizes");
+    GNNGP_REQUIRE(rowptr && C && panels && (nnz == 0 || (colidx && vals)), "spmm_panels: null pointer");
+    GNNGP_REQUIRE(n_cols < ((int64_t)1 << 24), "spmm_panels: too many columns for the panel addressing");
+    cudaStream_t st = as_stream(stream);
+    GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
+    if (nnz == 0) return GNNGP_OK;
+    int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : (nnz >= ((int64_t)1 << 25) ? 1024 : 512);
+    const int64_t n_tiles = ceil_div(k, PANEL);
+    while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * n_tiles < (int64_t)sm_count() * 32) chunk >>= 1;
+    const int64_t n_chunks = ceil_div(nnz, chunk);
+    const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
+    GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm_panels: grid of %lld blocks is too large", (long long)blocks);
+    spmm_panel_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k, alpha, C,
+                                                                    ldc, chunk, n_chunks, n_tiles);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
 }
 
 extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows,

@@ -205,6 +205,24 @@ class CudaOps(object):
                       self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), wptr, need, self._stream())
         return out
 
+    def panels_from_peers(self, peer_ptrs_dev: int, world: int, rows_per_rank: int, ld: int, n: int, k: int, device) -> torch.Tensor:
+        """64-column panels of the [n x k] operand whose row blocks live in the peers' memory (NVLink pull)."""
+        need = self.lib.query("gnngp_spmm_workspace_bytes", n, k)
+        ws = self.workspace(need + 256, device, "spmm")
+        wptr = (ws.data_ptr() + 255) // 256 * 256
+        self.lib.call("gnngp_panelize_peers_f32", peer_ptrs_dev, int(world), int(rows_per_rank), int(ld), int(n), int(k), wptr,
+                      self._stream())
+        return ws, wptr
+
+    def spmm_panels(self, csr: CsrMatrix, panels_ptr: int, k: int, alpha: float, out: torch.Tensor) -> torch.Tensor:
+        self._check(out, "out", dims=2)
+        if out.shape != (csr.n_rows, k) or (k > 1 and out.stride(1) != 1):
+            raise RuntimeError("spmm_panels: out must be a [%d x %d] row-major view" % (csr.n_rows, k))
+        self.lib.call("gnngp_spmm_panels_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(), csr.n_rows,
+                      csr.n_cols, csr.nnz, panels_ptr, k, float(alpha), out.data_ptr(), self._ld(out),
+                      int(self.spmm_nnz_per_warp), self._stream())
+        return out
+
     # ------------------------------------------------------------------ dense contractions
     def _gemm_ws(self, M: int, N: int, K: int, device):
         need = self.lib.query("gnngp_gemm_workspace_bytes", M, N, K)

@@ -227,8 +227,20 @@ class Pipeline(object):
         return self.propagate(csr, self.relu_nystrom(q, land), alpha, out=out)
 
     def propagate(self, csr, block: torch.Tensor, alpha: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``alpha * A @ X`` for this rank's rows of A: all-gather X's row blocks, then the CSR SpMM."""
-        full = self.comm.all_gather_rows(block, self._layout(block.shape[0]))
+        """``alpha * A @ X`` for this rank's rows of A.  Single rank: the CSR SpMM.  Sharded: the row blocks
+        of X are pulled from the peers into the SpMM's panel layout by one kernel over NVLink when the
+        communicator offers it (dense-row graphs), else NCCL all-gather followed by the SpMM."""
+        layout = self._layout(block.shape[0])
+        pull = getattr(self.comm, "pull_panels", None)
+        k = block.shape[1]
+        if pull is not None and block.is_cuda and csr.nnz >= 64 * csr.n_rows and k >= 256:
+            got = pull(self.ops, block, layout)
+            if got is not None:
+                workspace, panels = got
+                if out is None:
+                    out = self.ops.empty(csr.n_rows, k, block.device)
+                return self.ops.spmm_panels(csr, panels, k, alpha, out)
+        full = self.comm.all_gather_rows(block, layout)
         return self.ops.spmm(csr, full, alpha, out=out)
 
     # ------------------------------------------------------------------ initial factor / kernel

@@ -20,6 +20,8 @@ exact (non-Nystrom) path is small (N ≤ 2 708 in the configs) and is not sharde
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Optional, Union
 
 import torch
@@ -43,6 +45,44 @@ class TorchComm(object):
         self.rank = dist.get_rank(group)
         self.bytes_gathered = 0
         self.bytes_reduced = 0
+        self.bytes_pulled = 0
+        # fused peer-memory gather (NVLink P2P loads inside our own kernel) instead of an NCCL all-gather;
+        # needs torch symmetric memory on an NCCL group.  GNNGP_PEER_GATHER=0 forces the NCCL path.
+        self.peer_gather = (os.environ.get("GNNGP_PEER_GATHER", "1") == "1" and torch.cuda.is_available()
+                            and dist.get_backend(group) == "nccl")
+        self._symm = {}
+
+    def _symmetric_block(self, rows: int, ld: int, device):
+        key = (rows, ld)
+        if key not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty((rows, ld), dtype=torch.float32, device=device)
+            handle = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            self._symm[key] = (buf, handle)
+        return self._symm[key]
+
+    def pull_panels(self, ops, block: Tensor, layout: RowLayout):
+        """Fused all-gather + panel layout for the sparse product: every rank publishes its row block in a
+        symmetric-memory buffer, then ONE kernel per rank pulls all blocks over NVLink straight into the
+        64-column panels its SpMM gathers from (no gathered [N x k] buffer, no NCCL call).  Returns
+        (workspace tensor, panel pointer) or None when symmetric memory is unavailable (→ NCCL all-gather)."""
+        if not self.peer_gather:
+            return None
+        n_local, k = block.shape
+        ld = _round_up(max(k, 1), 4)
+        try:
+            buf, handle = self._symmetric_block(layout.rows_per_rank, ld, block.device)
+        except Exception as exc:           # same environment on every rank: all of them land here together
+            warnings.warn("gnngp_b200: symmetric memory unavailable (%r); using the NCCL all-gather" % (exc,))
+            self.peer_gather = False
+            return None
+        buf[:n_local, :k].copy_(block)
+        handle.barrier(channel=0)                          # every rank's block is published
+        ws, ptr = ops.panels_from_peers(handle.buffer_ptrs_dev, self.world, layout.rows_per_rank, ld, layout.n, k,
+                                        block.device)
+        handle.barrier(channel=1)                          # every rank has finished reading before a block is reused
+        self.bytes_pulled += (self.world - 1) * layout.rows_per_rank * k * 4
+        return ws, ptr
 
     def all_reduce_sum(self, t: Tensor) -> Tensor:
         if t.is_contiguous():

@@ -43,7 +43,8 @@ def compare(name, data, masks, nugget, hyper):
                "fit_mid_rel": float((fit[50] - ref[50]).norm() / ref[50].norm()),
                "val_curve_maxdiff": float((res["val"] - single.result["val"]).abs().max()),
                "test_curve_maxdiff": float((res["test"] - single.result["test"]).abs().max()),
-               "gathered_GB": sharded.comm.bytes_gathered / 1e9, "reduced_GB": sharded.comm.bytes_reduced / 1e9}
+               "gathered_GB": sharded.comm.bytes_gathered / 1e9, "reduced_GB": sharded.comm.bytes_reduced / 1e9,
+               "pulled_over_nvlink_GB": sharded.comm.bytes_pulled / 1e9, "peer_gather": bool(sharded.comm.peer_gather)}
         report[name] = row
         print(name, json.dumps(row), flush=True)
     dist.barrier()
@@ -58,6 +59,12 @@ for name in ("small-GCN-nys4-L2", "small-SAGE-nys4-L4", "pubmed-GCN-nys4-L2", "p
 data = synth.make_graph("arxiv", seed=0, device=dev)
 land = synth.draw_landmarks(data.train_mask, 50, seed=0)
 compare("arxiv-f50", data, {"landmark": land}, synth.nugget_grid(dev), dict(L=2, sigma_b=0.0, sigma_w=1.0, method="GCN"))
+if "--reddit" in sys.argv:
+    del data
+    torch.cuda.empty_cache()
+    data = synth.make_graph("reddit", seed=0, device=dev)
+    land = synth.draw_landmarks(data.train_mask, 50, seed=0)
+    compare("reddit-f50", data, {"landmark": land}, synth.nugget_grid(dev), dict(L=2, sigma_b=0.0, sigma_w=1.0, method="GCN"))
 if rank == 0:
     with open(os.path.join(ROOT, "gpurun_out", "multigpu_check_n%d.json" % world), "w") as fh:
         json.dump(report, fh, indent=1)
