@@ -285,7 +285,7 @@ def run_ours(args):
     launches = (ops.launch_count() - launches0) // max(args.steps, 1)
     timer.enabled = False
     table = timer.summary()
-    spmm_calls = timer.calls("spmm")
+    spmm_calls = timer.calls("spmm") + timer.calls("spmm_panels")
 
     # ---- roofline of the dominant kernel: the layer-2 SpMM (largest k)
     peaks = {"hbm_gbs": 6650.0, "source": "fallback"}

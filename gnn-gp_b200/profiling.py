@@ -11,7 +11,7 @@ from typing import Dict, List
 
 import torch
 
-TIMED = ("csr_from_coo", "spmm", "gemm_nt", "syrk", "restrict_columns", "gram_arccos", "initial_kernel", "nugget_coeff", "nugget_sweep", "row_norms",
+TIMED = ("csr_from_coo", "spmm", "spmm_panels", "panels_from_peers", "gemm_nt", "syrk", "restrict_columns", "gram_arccos", "initial_kernel", "nugget_coeff", "nugget_sweep", "row_norms",
          "gather_rows", "scatter_rows", "gather_rows_t", "gather_cols", "affine", "eigh", "nystrom_spectrum",
          "scale_cols", "arccos_dense", "onehot_t", "argmax_count", "sqerr_sum", "mean", "fill_col")
 
@@ -37,6 +37,8 @@ class OpTimer(object):
             info = None
             if name == "spmm":
                 info = (args[0].n_rows, args[0].nnz, int(args[1].shape[1]))
+            elif name == "spmm_panels":
+                info = (args[0].n_rows, args[0].nnz, int(args[2]))
             elif name in ("gemm_nt", "gram_arccos"):
                 info = (int(args[0].shape[0]), int(args[1].shape[0]), int(args[0].shape[1]))
             elif name == "nugget_sweep":
