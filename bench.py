@@ -310,6 +310,22 @@ def run_ours(args):
                 "l2_gather_bytes": gather_bytes, "l2_gather_tbs": round(gather_bytes / (ms * 1e-3) / 1e12, 3),
                 "fp32_tflops": round(2.0 * nnz * k / (ms * 1e-3) / 1e12, 2)}
 
+    # ---- tensor-core side: the fused Gram + arc-cosine contraction (largest tcgen05 launch of the recursion)
+    roof_tensor = None
+    gram_calls = [(i, ms) for i, ms in timer.calls("gram_arccos") if i is not None]
+    if gram_calls:
+        work = max(i[0] * i[1] * i[2] for i, _ in gram_calls)
+        big = [(i, ms) for i, ms in gram_calls if i[0] * i[1] * i[2] == work]
+        (gm, gn, gk), _ = big[0]
+        gms = sum(m for _, m in big) / len(big)
+        useful = 2.0 * gm * gn * gk / (gms * 1e-3) / 1e12
+        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+        roof_tensor = {"bound": "tensor", "kernel": "gemm_nt_tc3_kernel<EpiArccos> (%d x %d x %d, 3xTF32)" % (gm, gn, gk),
+                       "achieved": round(useful, 1), "issued_tflops": round(3 * useful, 1), "peak": round(tf32_peak, 1),
+                       "peak_source": "%s bf16 burst / 2 (TF32)" % peaks["source"], "unit": "TFLOP/s",
+                       "frac": round(3 * useful / tf32_peak, 4), "ms_per_launch": round(gms, 3),
+                       "note": "useful flops x 3 MMAs per product (fp32-equivalent split) against the TF32 rate"}
+
     # ---- end to end from pinned host buffers through the public API (N = 1 path; sharded: each rank its copy)
     e2e = None
     if not args.no_e2e:
@@ -366,7 +382,8 @@ def run_ours(args):
                     info["nnz"] * 8 / 1e9, info["nodes"] * (info["landmarks"] + 1) * 4 / 1e9),
                     "parallelism": "row-sharded x%d" % world if world > 1 else "single GPU",
                     "best": {k: float(summary[k]) for k in ("train", "val", "test", "nugget")}},
-                "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_tensor": roof_tensor,
+                "cpu_baseline": cpu,
                 "stages_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}}
         if args.breakdown:
             with open(args.breakdown, "w") as fh:

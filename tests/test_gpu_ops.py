@@ -258,3 +258,25 @@ def test_argmax_count_variants(ops, ref, n, C, G):
     member = torch.randint(0, 16, (n,), generator=g).to(torch.uint8)
     got = ops.argmax_count(f.cuda(), y.cuda(), member.cuda()).cpu()
     assert torch.equal(got, ref.argmax_count(f, y, member))
+
+
+def test_panel_entry_points_single_rank(ops, ref):
+    """gnngp_panelize_peers_f32 + gnngp_spmm_panels_f32 with a 'world' of two blocks living on this GPU."""
+    n, k = 3001, 300
+    row, col, val = rand_graph(n, 400000, seed=9, hub=5)
+    csr = ops.csr_from_coo(row.cuda(), col.cuda(), val.cuda(), n, n)
+    cref = ref.csr_from_coo(row, col, val, n, n)
+    g = torch.Generator().manual_seed(1)
+    b = torch.randn(n, k, generator=g)
+    rpr = (n + 1) // 2
+    ld = 300
+    blocks = [torch.zeros(rpr, ld).cuda() for _ in range(2)]
+    blocks[0][:rpr] = b[:rpr].cuda()
+    blocks[1][: n - rpr] = b[rpr:].cuda()
+    ptrs = torch.tensor([blk.data_ptr() for blk in blocks], dtype=torch.int64).cuda()
+    ws, panels = ops.panels_from_peers(ptrs.data_ptr(), 2, rpr, ld, n, k, b.cuda().device)
+    out = torch.full((n, k + 3), 5.0).cuda()
+    ops.spmm_panels(csr, panels, k, 0.5, out[:, 1:1 + k])
+    want = ref.spmm(cref, b, 0.5)
+    assert rel(out[:, 1:1 + k], want) < TOL
+    assert bool((out[:, 0] == 5.0).all()) and bool((out[:, 1 + k:] == 5.0).all())
