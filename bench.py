@@ -125,7 +125,7 @@ def cpu_sampled_baseline(args, data=None, land_mask=None) -> dict:
         # Reddit shape that is ~115 M edges; the sample only needs `rows` adjacency rows, so a graph with the
         # same degree law restricted to the sampled rows is drawn instead (same nnz per row in expectation).
         data, land_mask = host_sample_graph(args, spec)
-    rows_wanted = args.cpu_sample_rows or max(256, min(n, int(n * 1.6e7 / max(1, data["nnz_total"]))))
+    rows_wanted = args.cpu_sample_rows or max(256, min(n, int(n * 3.2e7 / max(1, data["nnz_total"]))))
     rng = np.random.default_rng(args.seed)
     pick = np.sort(rng.choice(n, size=min(rows_wanted, n), replace=False))
     indptr, indices, vals = data["rows_csr"](pick)
@@ -133,7 +133,7 @@ def cpu_sampled_baseline(args, data=None, land_mask=None) -> dict:
     x = data["x"]
     land_idx = np.nonzero(land_mask)[0]
     n_land = int(land_idx.shape[0])
-    dense_rows = int(min(n, max(4096, min(32768, n // 8))))
+    dense_rows = int(min(n, max(4096, min(65536, n // 4))))
     threads = orc._native().oracle_num_threads() if orc._native() is not None else 1
     est = sampled.estimate_gcn_nystrom_seconds(sample, n, x, x[land_idx] if n_land >= f else np.zeros((n_land, f), np.float32),
                                                n_land, n_train, c, 101, args.layers, args.sigma_b, args.sigma_w,
