@@ -274,49 +274,60 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
     }
     int64_t row = lo;
 
+    // Everything inside the work item is addressed relative to p0 with 32-bit integers (a work item holds at
+    // most a few thousand nonzeros): ncu showed the 64-bit bookkeeping made the kernel issue-bound (81 % of
+    // issue slots, 36 instructions per pair of nonzeros).  64-bit arithmetic remains once per row only.
+    const int len = (int)(p1 - p0);
+    const int32_t *cols = colidx + p0;
+    const float *vs = vals + p0;
+
     // The (colidx, vals) stream of the work item is consumed in batches of 32 that do not depend on row
     // boundaries; the batch after the current one is already in registers (software prefetch), so the
     // HBM latency of the adjacency stream overlaps the gathers of the current batch.
-    auto fetch = [&](int64_t at) {
+    auto fetch = [&](int at) {
         int2 e = make_int2(0, 0);
-        const int64_t mine = at + lane;
-        if (mine < p1) {
-            e.x = __ldcs(colidx + mine);
-            e.y = __float_as_int(__ldcs(vals + mine));
+        const int mine = at + lane;
+        if (mine < len) {
+            e.x = __ldcs(cols + mine);
+            e.y = __float_as_int(__ldcs(vs + mine));
         }
         return e;
     };
-    int64_t batch = p0;                                   // first nonzero of the staged batch
-    int2 ahead = fetch(p0 + 32);
-    stage[lane] = fetch(p0);
+    // one 64-bit register holds the lane's panel base, so a gather address is a single IMAD.WIDE (col * 256 + base)
+    uint64_t base64 = reinterpret_cast<uint64_t>(base);
+    asm volatile("" : "+l"(base64));
+    auto gather = [&](int col) {
+        return __ldg(reinterpret_cast<const float4 *>(base64 + (uint64_t)(uint32_t)col * 256u));   // n_cols < 2^24
+    };
+    int batch = 0;                                        // first nonzero (relative) of the staged batch
+    int2 ahead = fetch(32);
+    stage[lane] = fetch(0);
     __syncwarp();
 
-    int64_t p = p0;
-    while (p < p1) {
+    int pos = 0;
+    while (pos < len) {
         int64_t rend = __ldg(rowptr + row + 1);
-        while (rend <= p) { ++row; rend = __ldg(rowptr + row + 1); }
+        while (rend <= p0 + pos) { ++row; rend = __ldg(rowptr + row + 1); }
         const int64_t rstart = __ldg(rowptr + row);
-        const int64_t seg_end = min(rend, p1);
+        const int seg_end = (int)min(rend - p0, (int64_t)len);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        while (p < seg_end) {
-            if (p >= batch + 32) {                        // advance the staged batch
+        while (pos < seg_end) {
+            if (pos >= batch + 32) {                      // advance the staged batch
                 batch += 32;
                 __syncwarp();
                 stage[lane] = ahead;
                 __syncwarp();
                 ahead = fetch(batch + 32);
             }
-            const int first = (int)(p - batch);
-            const int last = (int)min((int64_t)32, seg_end - batch);
-            const int full = first + (last - first) / GROUP * GROUP;
-            for (int j = first; j < full; j += GROUP) {
+            const int last = min(32, seg_end - batch);
+            int j = pos - batch;
+            for (; j + GROUP <= last; j += GROUP) {       // 16 nonzeros per step: 8 gathers in flight per lane
                 int2 ent[kPanelUnroll];
                 float4 b[kPanelUnroll];
 #pragma unroll
                 for (int u = 0; u < kPanelUnroll; ++u) ent[u] = stage[j + u * 2 + sub];
 #pragma unroll
-                for (int u = 0; u < kPanelUnroll; ++u)
-                    b[u] = __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent[u].x << 8)));
+                for (int u = 0; u < kPanelUnroll; ++u) b[u] = gather(ent[u].x);
 #pragma unroll
                 for (int u = 0; u < kPanelUnroll; ++u) {
                     const float v = __int_as_float(ent[u].y);
@@ -324,27 +335,24 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
                     acc.z = fmaf(v, b[u].z, acc.z); acc.w = fmaf(v, b[u].w, acc.w);
                 }
             }
-            // ragged remainder (< 16 nonzeros): all loads first, then the FMAs
-            {
-                int2 ent[kPanelUnroll];
-                float4 b[kPanelUnroll];
+            for (; j < last; j += 8) {                    // ragged remainder, 8 nonzeros at a time, predicated
+                int2 ent[4];
+                float4 b[4];
 #pragma unroll
-                for (int u = 0; u < kPanelUnroll; ++u) {
-                    const int j = full + u * 2 + sub;
-                    ent[u] = (j < last) ? stage[j] : make_int2(-1, 0);
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = j + u * 2 + sub;
+                    ent[u] = (jj < last) ? stage[jj] : make_int2(-1, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < kPanelUnroll; ++u)
-                    b[u] = (ent[u].x >= 0) ? __ldg(reinterpret_cast<const float4 *>(base + ((uint64_t)(uint32_t)ent[u].x << 8)))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 4; ++u) b[u] = (ent[u].x >= 0) ? gather(ent[u].x) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < kPanelUnroll; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const float v = __int_as_float(ent[u].y);
                     acc.x = fmaf(v, b[u].x, acc.x); acc.y = fmaf(v, b[u].y, acc.y);
                     acc.z = fmaf(v, b[u].z, acc.z); acc.w = fmaf(v, b[u].w, acc.w);
                 }
             }
-            p = batch + last;
+            pos = batch + last;
         }
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
@@ -361,7 +369,7 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
                 }
             }
         }
-        if (seg_end == rend) ++row;
+        if ((int64_t)seg_end + p0 == rend) ++row;
     }
 }
 
