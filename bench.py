@@ -216,6 +216,20 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def ncu_traffic(kernel: str, info: dict, k: int):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json) — only when that capture was taken at the
+    SAME launch shape as the one timed here, else null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            rec = json.load(fh)[kernel]
+        if int(rec["nnz"]) == int(info["nnz"]) and int(rec["n"]) == int(info["nodes"]) and int(rec["k"]) == int(k):
+            return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from gnngp_b200 import synth
@@ -306,7 +320,7 @@ def run_ours(args):
         gather_bytes = 4.0 * nnz * k
         roof = {"bound": "hbm", "kernel": "spmm_panel_kernel (layer-2 propagation A @ E, k=%d)" % k, "achieved": round(achieved, 2),
                 "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 5),
-                "traffic": None, "ms_per_launch": round(ms, 3), "algorithmic_bytes": alg_bytes,
+                "traffic": ncu_traffic("spmm_panel_kernel", info, k), "ms_per_launch": round(ms, 3), "algorithmic_bytes": alg_bytes,
                 "l2_gather_bytes": gather_bytes, "l2_gather_tbs": round(gather_bytes / (ms * 1e-3) / 1e12, 3),
                 "fp32_tflops": round(2.0 * nnz * k / (ms * 1e-3) / 1e12, 2)}
 

@@ -308,28 +308,69 @@ class Pipeline(object):
             return self.propagate(csr, q0, 1.0)
         if method == "RBF":
             return q0
+        # After the first propagation only the first N_i columns (and the bias column) of the reference's
+        # [N x (N_a+1)] factor are non-zero (src/compute.py:141-143: ``Q[:, :N_i] = ...`` into zeros).  When
+        # N_i < N_a the first ReLU expectation therefore contracts over a COMPACT [N x (N_i+1)] factor —
+        # the zero columns add exactly 0 to every Gram entry and row norm — instead of N_a+1 columns
+        # (Reddit shape, fraction 50: 603 instead of 3 025; arxiv shape, fraction 10: 129 instead of 9 095).
+        compact = layers > 1 and ni < na
         if method == "GCN":
-            q = ops.zeros(n, na + 1, dev)
-            self.propagate(csr, q0, sigma_w, out=q[:, :ni])
-            ops.fill_col(q, na, sigma_b)
-            for _ in range(layers - 1):
+            if compact:
+                q1 = ops.zeros(n, ni + 1, dev)
+                self.propagate(csr, q0, sigma_w, out=q1[:, :ni])
+                ops.fill_col(q1, ni, sigma_b)
+                q = ops.zeros(n, na + 1, dev)
+                self._layer(q1, land, csr, sigma_w, q[:, :na])
+                del q1
+                ops.fill_col(q, na, sigma_b)
+                first = 1
+            else:
+                q = ops.zeros(n, na + 1, dev)
+                self.propagate(csr, q0, sigma_w, out=q[:, :ni])
+                ops.fill_col(q, na, sigma_b)
+                first = 0
+            for _ in range(first, layers - 1):
                 self._layer(q, land, csr, sigma_w, q[:, :na])
                 ops.fill_col(q, na, sigma_b)
             return q
         if method == "GIN":
-            q = ops.zeros(n, na + 1, dev)
-            self.propagate(csr, q0, sigma_w, out=q[:, :ni])
-            ops.fill_col(q, na, sigma_b)
-            for _ in range(layers - 1):
+            if compact:
+                q1 = ops.zeros(n, ni + 1, dev)
+                self.propagate(csr, q0, sigma_w, out=q1[:, :ni])
+                ops.fill_col(q1, ni, sigma_b)
+                e = self.relu_nystrom(q1, land)
+                del q1
+                q = ops.zeros(n, na + 1, dev)
+                ops.affine(q[:, :na], e, None, sigma_w, 0.0, 0.0)
+                ops.fill_col(q, na, sigma_b)
+                first = 1
+            else:
+                q = ops.zeros(n, na + 1, dev)
+                self.propagate(csr, q0, sigma_w, out=q[:, :ni])
+                ops.fill_col(q, na, sigma_b)
+                first = 0
+            for _ in range(first, layers - 1):
                 e = self.relu_nystrom(q, land)
                 ops.affine(q[:, :na], e, None, sigma_w, 0.0, 0.0)
                 ops.fill_col(q, na, sigma_b)
             return q
         if method == "SAGE":
-            q = ops.zeros(n, 2 * na, dev)
-            ops.affine(q[:, :ni], q0, None, sigma_b, 0.0, 0.0)
-            self.propagate(csr, q0, sigma_w, out=q[:, ni:2 * ni])
-            for _ in range(layers - 1):
+            if compact:
+                q1 = ops.zeros(n, 2 * ni, dev)
+                ops.affine(q1[:, :ni], q0, None, sigma_b, 0.0, 0.0)
+                self.propagate(csr, q0, sigma_w, out=q1[:, ni:])
+                e = self.relu_nystrom(q1, land)
+                del q1
+                q = ops.zeros(n, 2 * na, dev)
+                ops.affine(q[:, :na], e, None, sigma_b, 0.0, 0.0)
+                self.propagate(csr, e, sigma_w, out=q[:, na:])
+                first = 1
+            else:
+                q = ops.zeros(n, 2 * na, dev)
+                ops.affine(q[:, :ni], q0, None, sigma_b, 0.0, 0.0)
+                self.propagate(csr, q0, sigma_w, out=q[:, ni:2 * ni])
+                first = 0
+            for _ in range(first, layers - 1):
                 e = self.relu_nystrom(q, land)
                 ops.affine(q[:, :na], e, None, sigma_b, 0.0, 0.0)
                 self.propagate(csr, e, sigma_w, out=q[:, na:])
