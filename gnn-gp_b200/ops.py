@@ -414,6 +414,16 @@ class CudaOps(object):
         evals, evecs = torch.linalg.eigh(src.to(self.eigh_dtype))
         return evals.to(torch.float32), evecs.to(torch.float32)
 
+    def shifted_solves(self, gram: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.Tensor):
+        """``X_i = (gram + shifts[i] I)⁻¹ rhs`` for every shift, by fp64 Cholesky (cuSOLVER potrf / potrs through
+        torch — library calls like ``eigh``, used by the nugget-parallel fit of the sharded mode).  ``gram`` is
+        fp32 with a meaningful LOWER triangle (like ``syrk``'s output), ``rhs_t`` is [C x m].  Returns the
+        solutions transposed and stacked, fp32 [(len(shifts)*C) x m], and the number of factorisations that
+        reported a non-positive pivot (device scalar; no host sync here)."""
+        self._check(gram, "gram", dims=2)
+        self._check(rhs_t, "rhs_t", dims=2)
+        return _shifted_solves(self, gram, rhs_t, shifts)
+
     def nystrom_spectrum(self, D: torch.Tensor):
         D = self._vec(D, "D")
         root = torch.empty_like(D)
@@ -481,3 +491,20 @@ def default_ops() -> CudaOps:
     if _OPS is None:
         _OPS = CudaOps()
     return _OPS
+
+
+def _shifted_solves(ops, gram: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.Tensor):
+    m, c = gram.shape[0], rhs_t.shape[0]
+    low = torch.tril(gram).to(torch.float64)
+    sym = low + torch.tril(low, -1).T
+    del low
+    rhs = rhs_t.to(torch.float64).T.contiguous()                     # [m x C]
+    base = sym.diagonal().clone()
+    out = ops.empty(int(shifts.numel()) * c, m, gram.device)
+    bad = torch.zeros((), dtype=torch.int64, device=gram.device)
+    for i in range(int(shifts.numel())):
+        sym.diagonal().copy_(base + shifts[i])
+        factor, info = torch.linalg.cholesky_ex(sym)
+        bad += (info != 0).to(torch.int64).sum()
+        out[i * c:(i + 1) * c] = torch.cholesky_solve(rhs, factor).T.to(torch.float32)
+    return out, bad

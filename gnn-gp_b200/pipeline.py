@@ -233,7 +233,10 @@ class Pipeline(object):
         layout = self._layout(block.shape[0])
         pull = getattr(self.comm, "pull_panels", None)
         k = block.shape[1]
-        if pull is not None and block.is_cuda and csr.nnz >= 64 * csr.n_rows and k >= 256:
+        # the choice of exchange must be the same on every rank (a barrier on one side, an NCCL call on the
+        # other would deadlock): it is made on the GLOBAL average degree, not on this rank's rows
+        nnz_total, n_total = getattr(self, "global_nnz", None) or (csr.nnz, csr.n_rows)
+        if pull is not None and block.is_cuda and nnz_total >= 64 * n_total and k >= 256:
             got = pull(self.ops, block, layout)
             if got is not None:
                 workspace, panels = got
@@ -476,9 +479,57 @@ class Pipeline(object):
             comm.all_reduce_sum(gram)
             comm.all_reduce_sum(qty_t)
             comm.all_reduce_sum(scale)
+        if self._fit_solver(gram.shape[0], nugget.numel()) == "cholesky":
+            fitted = self._fit_by_shifted_solves(q, gram, qty_t, scale, nugget, trailing)
+            if fitted is not None:
+                return fitted
         evals, evecs = ops.eigh(gram)
         proj_t = ops.gemm_nt(qty_t, ops.transpose(evecs))             # (V^T Q_b^T y_b)^T  [C x m]
         return self._sweep(q, evals, evecs, proj_t, scale, nugget, trailing)
+
+    def _fit_solver(self, m: int, n_nuggets: int) -> str:
+        """``eigh`` (the reference's algorithm, src/predict.py:57-62: one m x m eigendecomposition serves all
+        nuggets) or ``cholesky`` (nugget-parallel: every rank factorises ``Q_bᵀQ_b + eps d I`` for ITS share of
+        the nugget grid).  The eigendecomposition cannot be sharded and is replicated on every rank — the
+        Amdahl term of the sharded mode — whereas the per-nugget solves are independent; with G/W solves per
+        rank they win once m is large (B200, fp64, `profiles/r1/call19_eigh_probe.json`: eigh / (potrf + potrs)
+        = 15x at m = 3 025, 28x at 6 138, 43x at 15 344).  ``GNNGP_FIT_SOLVER`` = eigh | cholesky | auto."""
+        import os
+        mode = os.environ.get("GNNGP_FIT_SOLVER", "auto")
+        if mode in ("eigh", "cholesky"):
+            return mode
+        world = self.comm.world
+        if world < 2 or m < 4096:
+            return "eigh"
+        per_rank = (n_nuggets + world - 1) // world
+        return "cholesky" if per_rank < 0.8 * 15.0 * (m / 3025.0) ** 0.65 else "eigh"
+
+    def _fit_by_shifted_solves(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
+                               nugget: torch.Tensor, trailing):
+        """All nuggets' coefficient blocks ``(Q_bᵀQ_b + eps d I)⁻¹ Q_bᵀy_b`` by shifted Cholesky solves, the
+        nugget grid dealt round-robin over the ranks, then the same one-contraction sweep as the eigen path.
+        Mathematically identical to src/predict.py:57-62 (``V diag(1/(w+eps d)) Vᵀ`` IS that inverse).
+        Returns None — on every rank alike — when some shifted matrix is not numerically positive definite
+        (rounding noise of the fp32 Gram above the smallest shift); the caller then takes the eigen path."""
+        ops, comm = self.ops, self.comm
+        g, c, m = nugget.numel(), qty_t.shape[0], gram.shape[0]
+        mine = torch.arange(comm.rank, g, comm.world, device=q.device)
+        coeff_t = ops.zeros(g * c, m, q.device)                       # [(G*C) x m], rows g*C + class
+        failed = torch.zeros(1, device=q.device)
+        if mine.numel() > 0:
+            shifts = nugget[mine].to(torch.float64) * scale.to(torch.float64)
+            sol_t, bad = ops.shifted_solves(gram, qty_t, shifts)      # [(len*C) x m]
+            rows = (mine.view(-1, 1) * c + torch.arange(c, device=q.device).view(1, -1)).flatten()
+            ops.scatter_rows(coeff_t, rows.contiguous(), sol_t)
+            failed += bad.to(failed.dtype)
+        if comm.world > 1:
+            comm.all_reduce_sum(coeff_t)
+            comm.all_reduce_sum(failed)
+        if float(failed) > 0:
+            return None
+        fitted = ops.nugget_sweep(q, coeff_t, g, c)
+        fitted = fitted.reshape((g, q.shape[0]) + tuple(trailing))
+        return fitted[0] if g == 1 else fitted
 
     def fit_exact(self, k: torch.Tensor, y: torch.Tensor, train_rows: torch.Tensor, nugget: torch.Tensor,
                   num_classes: Optional[int] = None) -> torch.Tensor:

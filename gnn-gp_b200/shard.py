@@ -142,6 +142,9 @@ class ShardedGNNGP(object):
                                     val[keep].to(torch.float32).contiguous(), lay.n_local, self.N, lay.begin)
         self.X_local = self.X[lay.begin:lay.end].to(torch.float32).contiguous()
         self.pipe = Pipeline(ops, self.comm, lay)
+        total = torch.tensor([float(self.csr.nnz)], dtype=torch.float64, device=self.X_local.device)
+        self.comm.all_reduce_sum(total)
+        self.pipe.global_nnz = (int(total.item()), self.N)
 
     def set_hyper_param(self, L=None, sigma_b=None, sigma_w=None, Nystrom=None, initial=None, method=None, **params):
         for name, value in zip(self._HYPER, (L, sigma_b, sigma_w, Nystrom, initial, method)):

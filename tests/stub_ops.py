@@ -131,6 +131,18 @@ class StubOps(object):
     def eigh(self, M):
         return torch.linalg.eigh(M.contiguous())
 
+    def shifted_solves(self, gram, rhs_t, shifts):
+        m, c = gram.shape[0], rhs_t.shape[0]
+        sym = torch.tril(gram).double()
+        sym = sym + torch.tril(sym, -1).T
+        out = self.empty(int(shifts.numel()) * c, m)
+        bad = torch.zeros((), dtype=torch.int64)
+        for i in range(int(shifts.numel())):
+            factor, info = torch.linalg.cholesky_ex(sym + shifts[i] * torch.eye(m, dtype=torch.float64))
+            bad += int(info != 0)
+            out[i * c:(i + 1) * c] = torch.cholesky_solve(rhs_t.double().T.contiguous(), factor).T.float()
+        return out, bad
+
     def nystrom_spectrum(self, D):
         root = torch.sqrt(torch.clamp(D, 0))
         return root, root / torch.clamp(D, D[-1] * 1e-4)

@@ -38,3 +38,50 @@ def test_reassociated_layer_schedule_matches_reference(name, monkeypatch):
     data, masks, nugget = cases.build_inputs(case)
     out = runner.run_pipeline(StubOps(), case, data, masks, nugget)
     runner.check_against_golden(name, out, masks)
+
+
+@pytest.mark.parametrize("name", ["tiny-GCN-nys2-L3", "tinyreg-GIN-nys1-L3", "small-SAGE-nys4-L4"])
+def test_nugget_parallel_cholesky_fit_matches_reference(name, monkeypatch):
+    """The sharded mode's nugget-parallel fit (shifted Cholesky solves instead of the replicated
+    eigendecomposition, pipeline._fit_by_shifted_solves) is the same posterior mean: golden check."""
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "cholesky")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    out = runner.run_pipeline(StubOps(), case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+
+
+def test_fit_solver_policy(monkeypatch):
+    from gnngp_b200.pipeline import Pipeline
+
+    class Comm(object):
+        rank = 0
+
+        def __init__(self, world):
+            self.world = world
+
+    monkeypatch.delenv("GNNGP_FIT_SOLVER", raising=False)
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(15356, 101) == "eigh"        # one rank: one eigh beats 101 solves
+    assert Pipeline(StubOps(), Comm(8))._fit_solver(3025, 101) == "eigh"         # small block: eigh is cheap
+    assert Pipeline(StubOps(), Comm(8))._fit_solver(6138, 101) == "cholesky"
+    assert Pipeline(StubOps(), Comm(4))._fit_solver(15356, 101) == "cholesky"
+    assert Pipeline(StubOps(), Comm(2))._fit_solver(15356, 101) == "eigh"
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "cholesky")
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(100, 101) == "cholesky"
+
+
+def test_indefinite_shifted_gram_falls_back_to_eigh(monkeypatch):
+    """A Gram block whose rounding noise exceeds the smallest shift is not positive definite: the
+    nugget-parallel fit must report it (None) so that every rank takes the eigen path."""
+    from gnngp_b200.pipeline import Pipeline
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "cholesky")
+    ops = StubOps()
+    pipe = Pipeline(ops)
+    gram = torch.diag(torch.tensor([4.0, 1.0, -0.5]))
+    qty_t = torch.ones(2, 3)
+    q = torch.randn(5, 3)
+    got = pipe._fit_by_shifted_solves(q, gram, qty_t, torch.ones(1), torch.tensor([0.1, 1.0]), (2,))
+    assert got is None
+    ok = pipe._fit_by_shifted_solves(q, gram.abs(), qty_t, torch.ones(1), torch.tensor([0.1, 1.0]), (2,))
+    want = q @ torch.linalg.solve(gram.abs() + 0.1 * torch.eye(3), qty_t.T)
+    assert torch.allclose(ok[0], want, rtol=1e-5, atol=1e-6)

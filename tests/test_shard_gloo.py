@@ -21,7 +21,8 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, out_dir, solver="auto"):
+    os.environ["GNNGP_FIT_SOLVER"] = solver
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
     import cases
@@ -49,13 +50,16 @@ def _worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,name", [(2, "tiny-GCN-nys2-L3"), (2, "tiny-SAGE-nys2-L2"), (3, "tiny-GCN2-nys2-L2"),
-                                        (2, "tinyreg-GIN-nys1-L3"), (2, "tiny-GCN-nys8-L2"), (2, "tiny-GCN-nys2-arccos")])
-def test_sharded_matches_single_rank(tmp_path, world, name):
+@pytest.mark.parametrize("world,name,solver", [(2, "tiny-GCN-nys2-L3", "auto"), (2, "tiny-SAGE-nys2-L2", "auto"),
+                                               (3, "tiny-GCN2-nys2-L2", "auto"), (2, "tinyreg-GIN-nys1-L3", "auto"),
+                                               (2, "tiny-GCN-nys8-L2", "auto"), (2, "tiny-GCN-nys2-arccos", "auto"),
+                                               # nugget-parallel fit: every rank solves its share of the nugget grid
+                                               (3, "tiny-GCN-nys2-L3", "cholesky"), (2, "tinyreg-GIN-nys1-L3", "cholesky")])
+def test_sharded_matches_single_rank(tmp_path, world, name, solver):
     import cases
     import runner
     from stub_ops import StubOps
-    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path), solver), nprocs=world, join=True)
     got = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
     case = cases.CASES[name]
     data, masks, nugget = cases.build_inputs(case)
