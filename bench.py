@@ -300,6 +300,7 @@ def run_ours(args):
     timer.enabled = False
     table = timer.summary()
     spmm_calls = timer.calls("spmm") + timer.calls("spmm_panels")
+    fit_solver = getattr(getattr(model, "pipe", None), "last_fit_solver", None) or "eigh"
 
     # ---- roofline of the dominant kernel: the layer-2 SpMM (largest k)
     peaks = {"hbm_gbs": 6650.0, "source": "fallback"}
@@ -408,6 +409,7 @@ def run_ours(args):
                 "config": {"workload": workload_name(args), "graph": info, "l2": "inputs larger than L2 (adjacency %.2f GB, factor %.2f GB)" % (
                     info["nnz"] * 8 / 1e9, info["nodes"] * (info["landmarks"] + 1) * 4 / 1e9),
                     "parallelism": "row-sharded x%d" % world if world > 1 else "single GPU",
+                    "fit_solver": fit_solver,
                     "best": {k: float(summary[k]) for k in ("train", "val", "test", "nugget")}},
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_tensor": roof_tensor,
                 "cpu_baseline": cpu,

@@ -44,7 +44,10 @@ def compare(name, data, masks, nugget, hyper):
                "val_curve_maxdiff": float((res["val"] - single.result["val"]).abs().max()),
                "test_curve_maxdiff": float((res["test"] - single.result["test"]).abs().max()),
                "gathered_GB": sharded.comm.bytes_gathered / 1e9, "reduced_GB": sharded.comm.bytes_reduced / 1e9,
-               "pulled_over_nvlink_GB": sharded.comm.bytes_pulled / 1e9, "peer_gather": bool(sharded.comm.peer_gather)}
+               "pulled_over_nvlink_GB": sharded.comm.bytes_pulled / 1e9, "peer_gather": bool(sharded.comm.peer_gather),
+               "fit_solver": getattr(sharded.pipe, "last_fit_solver", None),
+               "best_nugget_sharded_vs_single": [float(sharded.get_summary()["nugget"]), float(single.get_summary()["nugget"])],
+               "test_at_best_sharded_vs_single": [float(sharded.get_summary()["test"]), float(single.get_summary()["test"])]}
         report[name] = row
         print(name, json.dumps(row), flush=True)
     dist.barrier()
@@ -66,6 +69,7 @@ if "--reddit" in sys.argv:
     land = synth.draw_landmarks(data.train_mask, 50, seed=0)
     compare("reddit-f50", data, {"landmark": land}, synth.nugget_grid(dev), dict(L=2, sigma_b=0.0, sigma_w=1.0, method="GCN"))
 if rank == 0:
-    with open(os.path.join(ROOT, "gpurun_out", "multigpu_check_n%d.json" % world), "w") as fh:
+    tag = os.environ.get("GNNGP_CHECK_TAG", "")
+    with open(os.path.join(ROOT, "gpurun_out", "multigpu_check_n%d%s.json" % (world, tag)), "w") as fh:
         json.dump(report, fh, indent=1)
 dist.destroy_process_group()
