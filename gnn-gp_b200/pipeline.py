@@ -495,16 +495,17 @@ class Pipeline(object):
         the nugget grid).  The eigendecomposition cannot be sharded and is replicated on every rank — the
         Amdahl term of the sharded mode — whereas the per-nugget solves are independent; with G/W solves per
         rank they win once m is large (B200, fp64, `profiles/r1/call19_eigh_probe.json`: eigh / (potrf + potrs)
-        = 15x at m = 3 025, 28x at 6 138, 43x at 15 344).  ``GNNGP_FIT_SOLVER`` = eigh | cholesky | auto."""
+        = 15x at m = 3 025, 28x at 6 138, 43x at 15 344; measured end to end at N = 8, `profiles/r1/call21_*`:
+        fraction 10 4.82 s -> 3.22 s, fraction 50 0.134 s -> 0.126 s).  ``GNNGP_FIT_SOLVER`` = eigh | cholesky | auto."""
         import os
         mode = os.environ.get("GNNGP_FIT_SOLVER", "auto")
         if mode in ("eigh", "cholesky"):
             return mode
         world = self.comm.world
-        if world < 2 or m < 4096:
+        if world < 2 or m < 2048:
             return "eigh"
         per_rank = (n_nuggets + world - 1) // world
-        return "cholesky" if per_rank < 0.8 * 15.0 * (m / 3025.0) ** 0.65 else "eigh"
+        return "cholesky" if per_rank < 15.0 * (m / 3025.0) ** 0.65 else "eigh"
 
     def _fit_by_shifted_solves(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
                                nugget: torch.Tensor, trailing):
