@@ -424,6 +424,23 @@ class CudaOps(object):
         self._check(rhs_t, "rhs_t", dims=2)
         return _shifted_solves(self, gram, rhs_t, shifts)
 
+    def potrs_batched(self, factors: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
+        """``X_b = (L_b L_bᵀ)⁻¹ rhs`` for a stack of fp64 lower Cholesky factors [b, m, m] and one fp64
+        right-hand-side block [m, c], in one launch of ``potrs_batched_kernel``.  Returns fp64 [b, m, c]."""
+        self._check(factors, "factors", dtype=torch.float64, dims=3)
+        self._check(rhs, "rhs", dtype=torch.float64, dims=2)
+        b, m, m2 = factors.shape
+        if m != m2 or rhs.shape[0] != m:
+            raise ValueError("potrs_batched: factors %s do not match rhs %s" % (tuple(factors.shape), tuple(rhs.shape)))
+        factors = factors if factors.is_contiguous() else factors.contiguous()
+        rhs = rhs if rhs.is_contiguous() else rhs.contiguous()
+        c = rhs.shape[1]
+        ldx = (c + 7) // 8 * 8
+        out = torch.empty((b, m, ldx), dtype=torch.float64, device=factors.device)
+        self.lib.call("gnngp_potrs_batched_f64", factors.data_ptr(), m, m * m, rhs.data_ptr(), c, 0, out.data_ptr(), ldx,
+                      m * ldx, m, c, b, self._stream())
+        return out[:, :, :c]
+
     def nystrom_spectrum(self, D: torch.Tensor):
         D = self._vec(D, "D")
         root = torch.empty_like(D)
@@ -500,11 +517,19 @@ def _shifted_solves(ops, gram: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.
     del low
     rhs = rhs_t.to(torch.float64).T.contiguous()                     # [m x C]
     base = sym.diagonal().clone()
-    out = ops.empty(int(shifts.numel()) * c, m, gram.device)
+    count = int(shifts.numel())
+    out = ops.empty(count * c, m, gram.device)
     bad = torch.zeros((), dtype=torch.int64, device=gram.device)
-    for i in range(int(shifts.numel())):
-        sym.diagonal().copy_(base + shifts[i])
-        factor, info = torch.linalg.cholesky_ex(sym)
-        bad += (info != 0).to(torch.int64).sum()
-        out[i * c:(i + 1) * c] = torch.cholesky_solve(rhs, factor).T.to(torch.float32)
+    held = max(1, min(count, int(8e9) // max(1, m * m * 8)))          # factors kept at once: <= 8 GB
+    for s0 in range(0, count, held):
+        cnt = min(held, count - s0)
+        stack = torch.empty((cnt, m, m), dtype=torch.float64, device=gram.device)
+        for i in range(cnt):
+            sym.diagonal().copy_(base + shifts[s0 + i])
+            factor, info = torch.linalg.cholesky_ex(sym)             # cuSOLVER potrf
+            bad += (info != 0).to(torch.int64).sum()
+            stack[i].copy_(factor)
+        sol = ops.potrs_batched(stack, rhs)                           # [cnt, m, C] fp64, one launch for all factors
+        out[s0 * c:(s0 + cnt) * c] = sol.permute(0, 2, 1).reshape(cnt * c, m).to(torch.float32)
+        del stack, sol
     return out, bad

@@ -493,10 +493,13 @@ class Pipeline(object):
         """``eigh`` (the reference's algorithm, src/predict.py:57-62: one m x m eigendecomposition serves all
         nuggets) or ``cholesky`` (nugget-parallel: every rank factorises ``Q_bᵀQ_b + eps d I`` for ITS share of
         the nugget grid).  The eigendecomposition cannot be sharded and is replicated on every rank — the
-        Amdahl term of the sharded mode — whereas the per-nugget solves are independent; with G/W solves per
-        rank they win once m is large (B200, fp64, `profiles/r1/call19_eigh_probe.json`: eigh / (potrf + potrs)
-        = 15x at m = 3 025, 28x at 6 138, 43x at 15 344; measured end to end at N = 8, `profiles/r1/call21_*`:
-        fraction 10 4.82 s -> 3.22 s, fraction 50 0.134 s -> 0.126 s).  ``GNNGP_FIT_SOLVER`` = eigh | cholesky | auto."""
+        Amdahl term of the sharded mode — whereas the per-nugget solves are independent.  Cost per nugget on a
+        B200 in fp64: cuSOLVER potrf + this library's batched substitution kernel (`csrc/solve.cu`, all of the
+        rank's nuggets in one launch) = 1.7 ms at m = 3 025, 5.2 ms at 6 138, 47 ms at 15 356, against ONE eigh
+        of 52 / 238 / 2 243 ms (`profiles/r1/call19_eigh_probe.json`, `call22_potrs_probe.json`): the solves win
+        when G/W is below ~30 (m/3025)^0.3.  Measured end to end at N = 8 (`profiles/r1/call21_*`, with the
+        library potrs): fraction 10 4.82 s -> 3.22 s, fraction 50 0.134 s -> 0.126 s.
+        ``GNNGP_FIT_SOLVER`` = eigh | cholesky | auto."""
         import os
         mode = os.environ.get("GNNGP_FIT_SOLVER", "auto")
         if mode in ("eigh", "cholesky"):
@@ -505,7 +508,7 @@ class Pipeline(object):
         if world < 2 or m < 2048:
             return "eigh"
         per_rank = (n_nuggets + world - 1) // world
-        return "cholesky" if per_rank < 15.0 * (m / 3025.0) ** 0.65 else "eigh"
+        return "cholesky" if per_rank < 30.0 * (m / 3025.0) ** 0.3 else "eigh"
 
     def _fit_by_shifted_solves(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
                                nugget: torch.Tensor, trailing):

@@ -132,6 +132,17 @@ int gnngp_nugget_sweep_f32(const float *Q, int64_t ldq, int64_t n, int64_t m, co
 int gnngp_nugget_coeff_f32(const float *temp, int64_t ldt, const float *w, const float *eps, const float *d,
                            int64_t m, int64_t C, int64_t G, float *S, int64_t lds, gnngp_stream_t stream);
 
+/* Batched Cholesky substitution in fp64: X_b = (L_b L_b^T)^-1 B_b for b < batch, all in ONE launch.
+ * L: lower factors, row-major, leading dimension ldl, l_stride elements between factors (the strict upper
+ * triangle is not read); B: [m x nrhs] right-hand sides, b_stride between batches (0 = the same B for every
+ * factor); X: [m x nrhs] solutions, ldx (a multiple of 8, >= nrhs rounded up to 8; rows 16-byte aligned; the
+ * padding columns are scratch), x_stride.  X may not alias B.  Used by the nugget-parallel fit of the
+ * sharded mode: per nugget it is the coefficient block `v @ (temp / (w + eps*d))` of src/predict.py:61-62,
+ * i.e. (Q_b^T Q_b + eps d I)^-1 Q_b^T y_b, computed from a Cholesky factor instead of the replicated eigh. */
+int gnngp_potrs_batched_f64(const double *L, int64_t ldl, int64_t l_stride, const double *B, int64_t ldb,
+                            int64_t b_stride, double *X, int64_t ldx, int64_t x_stride, int64_t m, int64_t nrhs,
+                            int64_t batch, gnngp_stream_t stream);
+
 /* ---- row / column utilities -------------------------------------------------------------- */
 /* out[i] = sum_j Q[i][j]^2 (take_sqrt = 0) or its square root (1) — src/compute.py:124, src/predict.py:58. */
 int gnngp_row_sumsq_f32(const float *Q, int64_t ldq, int64_t n, int64_t m, int take_sqrt, float *out,

@@ -280,3 +280,42 @@ def test_panel_entry_points_single_rank(ops, ref):
     want = ref.spmm(cref, b, 0.5)
     assert rel(out[:, 1:1 + k], want) < TOL
     assert bool((out[:, 0] == 5.0).all()) and bool((out[:, 1 + k:] == 5.0).all())
+
+
+@pytest.mark.parametrize("m,nrhs,batch", [(1, 1, 1), (31, 7, 2), (32, 8, 1), (33, 9, 3), (100, 41, 2), (257, 3, 1),
+                                          (1000, 41, 4)])
+def test_potrs_batched_matches_cholesky_solve(ops, m, nrhs, batch):
+    """fp64 batched substitution kernel vs torch.cholesky_solve (cuSOLVER potrs); tolerance 1e-11 relative."""
+    g = torch.Generator().manual_seed(m * 100 + nrhs)
+    a = torch.randn(m, m + 5, generator=g, dtype=torch.float64)
+    spd = a @ a.T / (m + 5)
+    shifts = torch.logspace(-3, 0, batch, dtype=torch.float64)
+    factors = torch.stack([torch.linalg.cholesky(spd + s * torch.eye(m, dtype=torch.float64)) for s in shifts]).cuda()
+    # the kernel must not read the strict upper triangle: poison it
+    poison = torch.triu(torch.full((m, m), float("nan"), dtype=torch.float64), 1).cuda()
+    factors_poisoned = torch.where(torch.isnan(poison), poison, factors)
+    rhs = torch.randn(m, nrhs, generator=g, dtype=torch.float64).cuda()
+    got = ops.potrs_batched(factors_poisoned, rhs)
+    assert got.shape == (batch, m, nrhs)
+    for b in range(batch):
+        want = torch.cholesky_solve(rhs, factors[b])
+        assert rel(got[b], want) < 1e-11
+        resid = (spd.cuda() + shifts[b].cuda() * torch.eye(m, dtype=torch.float64, device="cuda")) @ got[b] - rhs
+        assert float(resid.norm() / rhs.norm()) < 1e-9
+
+
+def test_shifted_solves_match_stub(ops, ref):
+    """ops.shifted_solves (potrf through torch + the batched substitution kernel) vs the torch restatement."""
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(400, 150, generator=g)
+    gram = torch.tril(q.T @ q)                        # lower triangle only, like syrk's output
+    rhs_t = torch.randn(7, 150, generator=g)
+    shifts = torch.tensor([0.01, 0.3, 5.0], dtype=torch.float64)
+    want, bad_ref = ref.shifted_solves(gram, rhs_t, shifts)
+    got, bad = ops.shifted_solves(gram.cuda(), rhs_t.cuda(), shifts.cuda())
+    assert int(bad) == 0 and int(bad_ref) == 0
+    assert got.shape == want.shape and rel(got, want) < 1e-5
+    # an indefinite shifted matrix is reported, not hidden
+    _, bad = ops.shifted_solves(torch.diag(torch.tensor([1.0, -2.0, 3.0])).cuda(), torch.ones(2, 3).cuda(),
+                                torch.tensor([0.5], dtype=torch.float64).cuda())
+    assert int(bad) == 1

@@ -62,12 +62,12 @@ def test_fit_solver_policy(monkeypatch):
 
     monkeypatch.delenv("GNNGP_FIT_SOLVER", raising=False)
     assert Pipeline(StubOps(), Comm(1))._fit_solver(15356, 101) == "eigh"        # one rank: one eigh beats 101 solves
-    assert Pipeline(StubOps(), Comm(4))._fit_solver(3025, 101) == "eigh"         # 26 solves per rank cost more than one eigh
-    assert Pipeline(StubOps(), Comm(8))._fit_solver(3025, 101) == "cholesky"     # 13 solves per rank: measured 8 ms faster
-    assert Pipeline(StubOps(), Comm(8))._fit_solver(604, 101) == "eigh"          # small block: eigh is cheap
-    assert Pipeline(StubOps(), Comm(8))._fit_solver(6138, 101) == "cholesky"
-    assert Pipeline(StubOps(), Comm(4))._fit_solver(15356, 101) == "cholesky"
+    assert Pipeline(StubOps(), Comm(2))._fit_solver(3025, 101) == "eigh"         # 51 solves per rank cost more than one eigh
     assert Pipeline(StubOps(), Comm(2))._fit_solver(15356, 101) == "eigh"
+    assert Pipeline(StubOps(), Comm(4))._fit_solver(3025, 101) == "cholesky"     # 26 x 1.7 ms < 52 ms
+    assert Pipeline(StubOps(), Comm(8))._fit_solver(3025, 101) == "cholesky"
+    assert Pipeline(StubOps(), Comm(4))._fit_solver(15356, 101) == "cholesky"
+    assert Pipeline(StubOps(), Comm(8))._fit_solver(604, 101) == "eigh"          # small block: eigh is cheap
     monkeypatch.setenv("GNNGP_FIT_SOLVER", "cholesky")
     assert Pipeline(StubOps(), Comm(1))._fit_solver(100, 101) == "cholesky"
 
