@@ -510,25 +510,60 @@ def default_ops() -> CudaOps:
     return _OPS
 
 
+_SOLVER_STREAMS = {}
+
+
+def _solver_streams(device: torch.device, wanted: int):
+    """Side streams for the independent per-nugget factorisations (cached per device)."""
+    have = _SOLVER_STREAMS.setdefault(device.index, [])
+    while len(have) < wanted:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:wanted]
+
+
 def _shifted_solves(ops, gram: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.Tensor):
+    """potrf per shift (cuSOLVER through torch) then ONE batched substitution launch.  One potrf of a few
+    thousand rows is a chain of small kernels (1.4 ms at m = 3 025 = 6 TFLOP/s of fp64); the shifts are
+    independent, so they are issued round-robin on ``GNNGP_SOLVER_STREAMS`` (default 4) side streams; the
+    measured gain is modest (13 shifts at m = 3 025: 23.7 -> 19.2 ms, `profiles/r1/call25_potrs_probe.json`)
+    because the host launch rate of the ~150 small kernels per potrf is the limit."""
+    import os
     m, c = gram.shape[0], rhs_t.shape[0]
+    dev = gram.device
     low = torch.tril(gram).to(torch.float64)
     sym = low + torch.tril(low, -1).T
     del low
     rhs = rhs_t.to(torch.float64).T.contiguous()                     # [m x C]
-    base = sym.diagonal().clone()
     count = int(shifts.numel())
-    out = ops.empty(count * c, m, gram.device)
-    bad = torch.zeros((), dtype=torch.int64, device=gram.device)
-    held = max(1, min(count, int(8e9) // max(1, m * m * 8)))          # factors kept at once: <= 8 GB
+    out = ops.empty(count * c, m, dev)
+    bad = torch.zeros((), dtype=torch.int64, device=dev)
+    # factors kept at once: <= 40 GB (all 13 of a rank at m = 15 356; one substitution launch is bound by the
+    # latency of a CTA walking a factor, not by how many factors it covers, so fewer, larger launches win)
+    held = max(1, min(count, int(40e9) // max(1, m * m * 8)))
+    lanes = max(1, min(int(os.environ.get("GNNGP_SOLVER_STREAMS", "4")), held))
+    main = torch.cuda.current_stream(dev)
+    side = _solver_streams(dev, lanes) if lanes > 1 else [main]
     for s0 in range(0, count, held):
         cnt = min(held, count - s0)
-        stack = torch.empty((cnt, m, m), dtype=torch.float64, device=gram.device)
+        stack = torch.empty((cnt, m, m), dtype=torch.float64, device=dev)
+        infos = []
+        ready = torch.cuda.Event()
+        ready.record(main)
         for i in range(cnt):
-            sym.diagonal().copy_(base + shifts[s0 + i])
-            factor, info = torch.linalg.cholesky_ex(sym)             # cuSOLVER potrf
-            bad += (info != 0).to(torch.int64).sum()
-            stack[i].copy_(factor)
+            stream = side[i % len(side)]
+            if stream is not main:
+                stream.wait_event(ready)
+            with torch.cuda.stream(stream):
+                shifted = sym.clone()
+                shifted.diagonal().add_(shifts[s0 + i])
+                factor, info = torch.linalg.cholesky_ex(shifted)     # cuSOLVER potrf
+                stack[i].copy_(factor)
+                infos.append(info)
+                del shifted, factor
+        for stream in side:
+            if stream is not main:
+                main.wait_stream(stream)
+        bad += torch.stack([(info != 0).to(torch.int64).sum() for info in infos]).sum()
         sol = ops.potrs_batched(stack, rhs)                           # [cnt, m, C] fp64, one launch for all factors
         out[s0 * c:(s0 + cnt) * c] = sol.permute(0, 2, 1).reshape(cnt * c, m).to(torch.float32)
         del stack, sol

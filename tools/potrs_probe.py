@@ -26,7 +26,7 @@ def timeit(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 
 
-for m, batch in ((3025, 13), (3025, 26), (6138, 13), (15356, 4)):
+for m, batch in ((3025, 13),):
     g = torch.Generator(device=dev).manual_seed(0)
     a = torch.randn(m, m + 64, device=dev, dtype=torch.float64, generator=g)
     spd = a @ a.T / m
@@ -44,6 +44,28 @@ for m, batch in ((3025, 13), (3025, 26), (6138, 13), (15356, 4)):
     out["m=%d batch=%d" % (m, batch)] = row
     print(m, batch, json.dumps(row), flush=True)
     del spd, factor, stack, rhs, want, got
+    torch.cuda.empty_cache()
+# the whole per-rank solve (potrf on side streams + batched substitution) against the number of streams
+for m, count in ((3025, 13), (3025, 26), (6138, 13), (15356, 13)):
+    g = torch.Generator(device=dev).manual_seed(1)
+    q = torch.randn(m + 512, m, device=dev, generator=g)
+    gram = torch.tril(q.T @ q)
+    del q
+    rhs_t = torch.randn(41, m, device=dev, generator=g)
+    shifts = torch.logspace(-1, 2, count, device=dev, dtype=torch.float64)
+    row = {}
+    for lanes in (1, 2, 4, 8, 13):
+        os.environ["GNNGP_SOLVER_STREAMS"] = str(lanes)
+        row["streams=%d_ms" % lanes] = timeit(lambda: ops.shifted_solves(gram, rhs_t, shifts), reps=2)
+    os.environ["GNNGP_SOLVER_STREAMS"] = "1"
+    a, _ = ops.shifted_solves(gram, rhs_t, shifts)
+    os.environ["GNNGP_SOLVER_STREAMS"] = "8"
+    b, bad = ops.shifted_solves(gram, rhs_t, shifts)
+    row["streams8_vs_1_rel"] = float((a - b).norm() / a.norm())
+    row["bad"] = int(bad)
+    out["shifted_solves m=%d count=%d" % (m, count)] = row
+    print("shifted_solves", m, count, json.dumps(row), flush=True)
+    del gram, rhs_t, a, b
     torch.cuda.empty_cache()
 with open(os.path.join(ROOT, "gpurun_out", "potrs_probe.json"), "w") as fh:
     json.dump(out, fh, indent=1)
