@@ -66,6 +66,17 @@ def test_public_api_matches_live_oracle(name):
     assert abs(float(out["summary"]["val"]) - ref["summary"]["val"]) <= 2.5 / max(int(masks["val"].sum()), 1) + 2e-3
 
 
+@pytest.mark.parametrize("name", ["small-GCN-nys4-L2", "tinyreg-GIN-nys1-L3", "pubmed-GCN-nys4-L2", "chameleon-SAGE-nys1-L2"])
+def test_nugget_parallel_fit_matches_reference_golden(name, monkeypatch):
+    """The sharded mode's fit route (fp64 potrf per nugget + the batched substitution kernel) forced on one
+    GPU: same golden check as the eigen route — posterior means, argmax, accuracy / R² curves."""
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "cholesky")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    out, _ = run_public_api(case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+
+
 def test_zz_write_parity_report():
     """Collect the measured parity errors (committed under profiles/ by the builder)."""
     os.makedirs("gpurun_out", exist_ok=True)
