@@ -52,8 +52,13 @@ def _get_kernel(C0: Tensor, A: Tensor, L: int, sigma_b: float, sigma_w: float, m
 
 def _get_kernel_Nystrom(Q0: Tensor, A: Tensor, L: int, sigma_b: float, sigma_w: float, mask: Tensor, method: str,
                         **params) -> Tensor:
-    """Nystrom approx square root ``Q`` of the GNNGP kernel (reference ``src/compute.py:90-107``)."""
+    """Nystrom approx square root ``Q`` of the GNNGP kernel (reference ``src/compute.py:90-107``).
+    ``_product_cache`` (not a kernel parameter; passed by ``GNNGP`` when ``reuse_products`` is on) lets a
+    hyper-parameter sweep keep the first propagation ``A @ Q0``."""
     pipe = _pipeline()
+    cache = params.pop("_product_cache", None)
+    if cache is not None:
+        pipe.product_cache = cache
     return pipe.kernel_nystrom(_f32(Q0), pipe.ops.csr_of(A), L, sigma_b, sigma_w, _landmarks(mask), method, params)
 
 

@@ -3,6 +3,7 @@ and methods; ``src/gnngp.py:63-135``), computing on B200 through :mod:`gnngp_b20
 :mod:`gnngp_b200.predict`."""
 from __future__ import annotations
 
+import os
 from typing import Union
 
 import torch
@@ -29,6 +30,11 @@ class GNNGP(object):
         self.set_hyper_param(L, sigma_b, sigma_w, Nystrom, initial, method, **params)
         graph = data.to(device)
         self.N, self.X, self.y, self.A, self.mask = datasets.get_data(graph)
+        # Hyper-parameter sweeps (figure3.sh: L / sigma_b / sigma_w grids on one graph) can keep the first
+        # propagation A @ Q0 across set_hyper_param calls.  Opt-in — set the attribute or
+        # GNNGP_REUSE_PRODUCTS=1 — because the reference recomputes everything on every call.
+        self.reuse_products = os.environ.get("GNNGP_REUSE_PRODUCTS", "0") == "1"
+        self._product_cache = {}
 
     def set_hyper_param(self, L: int = None, sigma_b: float = None, sigma_w: float = None, Nystrom: bool = None,
                         initial: str = None, method: str = None, **params) -> None:
@@ -47,7 +53,8 @@ class GNNGP(object):
             land = self.mask["landmark"]
             self.Q0 = compute._init_kernel_Nystrom(self.X, land, self.initial, **p)
             self.Q = compute._get_kernel_Nystrom(self.Q0, self.A, self.L, self.sigma_b, self.sigma_w, land,
-                                                 self.method, **p)
+                                                 self.method, _product_cache=self._product_cache if self.reuse_products else None,
+                                                 **p)
         else:
             self.C0 = compute._init_kernel(self.X, self.initial, **p)
             self.K = compute._get_kernel(self.C0, self.A, self.L, self.sigma_b, self.sigma_w, self.method, **p)

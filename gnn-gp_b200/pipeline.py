@@ -246,6 +246,23 @@ class Pipeline(object):
         full = self.comm.all_gather_rows(block, layout)
         return self.ops.spmm(csr, full, alpha, out=out)
 
+    def first_product(self, csr, q0: torch.Tensor, alpha: float, out: torch.Tensor) -> torch.Tensor:
+        """``out = alpha * A @ Q0`` — the first propagation of every layer recursion (src/compute.py:142,
+        164, 186, 205).  It depends on the graph and the initial factor only, not on L / sigma_b / sigma_w /
+        method, so a hyper-parameter sweep (figure3.sh) can reuse it: when the caller attached a
+        ``product_cache`` dict (``GNNGP.reuse_products``) the unscaled product is kept and
+        later calls only rescale it.  Off by default: the reference recomputes it on every call, and so
+        does every timed step of bench.py."""
+        cache = getattr(self, "product_cache", None)
+        if cache is None:
+            return self.propagate(csr, q0, alpha, out=out)
+        key = (id(csr), q0.data_ptr(), tuple(q0.shape), q0._version)
+        hit = cache.get("first")
+        if hit is None or hit[0] != key:
+            hit = (key, self.propagate(csr, q0, 1.0), csr, q0)      # csr / q0 kept alive so the key stays unique
+            cache["first"] = hit
+        return self.ops.affine(out, hit[1], None, alpha, 0.0, 0.0)
+
     # ------------------------------------------------------------------ initial factor / kernel
     def initial_columns(self, x: torch.Tensor, ref_rows: torch.Tensor, initial: str, params: dict) -> torch.Tensor:
         ops = self.ops
@@ -320,7 +337,7 @@ class Pipeline(object):
         if method == "GCN":
             if compact:
                 q1 = ops.zeros(n, ni + 1, dev)
-                self.propagate(csr, q0, sigma_w, out=q1[:, :ni])
+                self.first_product(csr, q0, sigma_w, q1[:, :ni])
                 ops.fill_col(q1, ni, sigma_b)
                 q = ops.zeros(n, na + 1, dev)
                 self._layer(q1, land, csr, sigma_w, q[:, :na])
@@ -329,7 +346,7 @@ class Pipeline(object):
                 first = 1
             else:
                 q = ops.zeros(n, na + 1, dev)
-                self.propagate(csr, q0, sigma_w, out=q[:, :ni])
+                self.first_product(csr, q0, sigma_w, q[:, :ni])
                 ops.fill_col(q, na, sigma_b)
                 first = 0
             for _ in range(first, layers - 1):
@@ -339,7 +356,7 @@ class Pipeline(object):
         if method == "GIN":
             if compact:
                 q1 = ops.zeros(n, ni + 1, dev)
-                self.propagate(csr, q0, sigma_w, out=q1[:, :ni])
+                self.first_product(csr, q0, sigma_w, q1[:, :ni])
                 ops.fill_col(q1, ni, sigma_b)
                 e = self.relu_nystrom(q1, land)
                 del q1
@@ -349,7 +366,7 @@ class Pipeline(object):
                 first = 1
             else:
                 q = ops.zeros(n, na + 1, dev)
-                self.propagate(csr, q0, sigma_w, out=q[:, :ni])
+                self.first_product(csr, q0, sigma_w, q[:, :ni])
                 ops.fill_col(q, na, sigma_b)
                 first = 0
             for _ in range(first, layers - 1):
@@ -361,7 +378,7 @@ class Pipeline(object):
             if compact:
                 q1 = ops.zeros(n, 2 * ni, dev)
                 ops.affine(q1[:, :ni], q0, None, sigma_b, 0.0, 0.0)
-                self.propagate(csr, q0, sigma_w, out=q1[:, ni:])
+                self.first_product(csr, q0, sigma_w, q1[:, ni:])
                 e = self.relu_nystrom(q1, land)
                 del q1
                 q = ops.zeros(n, 2 * na, dev)
@@ -371,7 +388,7 @@ class Pipeline(object):
             else:
                 q = ops.zeros(n, 2 * na, dev)
                 ops.affine(q[:, :ni], q0, None, sigma_b, 0.0, 0.0)
-                self.propagate(csr, q0, sigma_w, out=q[:, ni:2 * ni])
+                self.first_product(csr, q0, sigma_w, q[:, ni:2 * ni])
                 first = 0
             for _ in range(first, layers - 1):
                 e = self.relu_nystrom(q, land)

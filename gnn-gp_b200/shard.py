@@ -142,6 +142,8 @@ class ShardedGNNGP(object):
                                     val[keep].to(torch.float32).contiguous(), lay.n_local, self.N, lay.begin)
         self.X_local = self.X[lay.begin:lay.end].to(torch.float32).contiguous()
         self.pipe = Pipeline(ops, self.comm, lay)
+        if os.environ.get("GNNGP_REUSE_PRODUCTS", "0") == "1":       # hyper-parameter sweeps: keep A @ Q0
+            self.pipe.product_cache = {}
         total = torch.tensor([float(self.csr.nnz)], dtype=torch.float64, device=self.X_local.device)
         self.comm.all_reduce_sum(total)
         self.pipe.global_nnz = (int(total.item()), self.N)

@@ -77,6 +77,36 @@ def test_nugget_parallel_fit_matches_reference_golden(name, monkeypatch):
     runner.check_against_golden(name, out, masks)
 
 
+def test_reuse_products_across_a_sweep_matches_fresh_models():
+    """SURVEY §8f N4 through the public API: with ``reuse_products`` a sigma_w / L sweep keeps A @ Q0 and
+    gives the same kernels and metrics as a fresh model per setting."""
+    from gnngp_b200.gnngp import GNNGP
+    from gnngp_b200.ops import default_ops
+    dev = torch.device("cuda:0")
+    case = cases.CASES["small-GCN-nys4-L2"]
+    data, masks, nugget = cases.build_inputs(case)
+    sweep = GNNGP(data, device=dev, Nystrom=True)
+    sweep.reuse_products = True
+    sweep.mask["landmark"] = masks["landmark"].to(dev)
+    ops = default_ops()
+    for layers, sigma_b, sigma_w in ((2, 0.0, 1.0), (3, 0.1, 1.4), (2, 0.2, 0.6)):
+        sweep.set_hyper_param(layers, sigma_b, sigma_w, method="GCN")
+        before = ops.launch_count()
+        sweep.predict(nugget.to(dev))
+        used = ops.launch_count() - before
+        fresh = GNNGP(data, device=dev, Nystrom=True)
+        fresh.mask["landmark"] = masks["landmark"].to(dev)
+        fresh.set_hyper_param(layers, sigma_b, sigma_w, method="GCN")
+        before = ops.launch_count()
+        fresh.predict(nugget.to(dev))
+        used_fresh = ops.launch_count() - before
+        a, b = sweep.Q[:300].double(), fresh.Q[:300].double()
+        assert float((a @ a.T - b @ b.T).norm() / (b @ b.T).norm()) < 1e-5
+        assert float((sweep.result["val"] - fresh.result["val"]).abs().max()) < 0.02
+        assert used > 0 and used_fresh > 0
+    assert "first" in sweep._product_cache
+
+
 def test_zz_write_parity_report():
     """Collect the measured parity errors (committed under profiles/ by the builder)."""
     os.makedirs("gpurun_out", exist_ok=True)

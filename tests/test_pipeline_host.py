@@ -87,3 +87,40 @@ def test_indefinite_shifted_gram_falls_back_to_eigh(monkeypatch):
     ok = pipe._fit_by_shifted_solves(q, gram.abs(), qty_t, torch.ones(1), torch.tensor([0.1, 1.0]), (2,))
     want = q @ torch.linalg.solve(gram.abs() + 0.1 * torch.eye(3), qty_t.T)
     assert torch.allclose(ok[0], want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["GCN", "GIN", "SAGE"])
+def test_first_product_reuse_across_hyper_parameters(method):
+    """with a product cache attached, a sigma_w / L sweep computes A @ Q0 once and the
+    results equal the uncached ones."""
+    from gnngp_b200.pipeline import Landmarks, Pipeline, RowLayout
+
+    class Counting(StubOps):
+        def __init__(self):
+            self.spmm_widths = []
+
+        def spmm(self, csr, B, alpha=1.0, out=None):
+            self.spmm_widths.append(int(B.shape[1]))
+            return StubOps.spmm(self, csr, B, alpha, out)
+
+    case = cases.CASES["tiny-GCN-nys2-L3"]
+    data, masks, _ = cases.build_inputs(case)
+    land = Landmarks(masks["landmark"], RowLayout(data.num_nodes))
+    ni = data.x.shape[1]
+    plain_ops, cached_ops = Counting(), Counting()
+    plain, cached = Pipeline(plain_ops), Pipeline(cached_ops)
+    cached.product_cache = {}
+    adj = torch.sparse_coo_tensor(data.edge_index, data.edge_attr, (data.num_nodes,) * 2)
+    csr_a, csr_b = plain_ops.csr_of(adj), cached_ops.csr_of(adj)
+    for layers, sigma_b, sigma_w in ((2, 0.1, 1.0), (3, 0.2, 1.3), (2, 0.0, 0.7)):
+        want = plain.kernel_nystrom(data.x, csr_a, layers, sigma_b, sigma_w, land, method, {})
+        got = cached.kernel_nystrom(data.x, csr_b, layers, sigma_b, sigma_w, land, method, {})
+        assert torch.allclose(want @ want.T, got @ got.T, rtol=2e-4, atol=1e-5)
+    assert plain_ops.spmm_widths.count(ni) == 3           # the reference's behaviour: once per call
+    assert cached_ops.spmm_widths.count(ni) == 1          # reused twice
+    # a different initial factor must not hit the cache
+    other = data.x * 2.0
+    got = cached.kernel_nystrom(other, csr_b, 2, 0.1, 1.0, land, method, {})
+    want = plain.kernel_nystrom(other, csr_a, 2, 0.1, 1.0, land, method, {})
+    assert torch.allclose(want @ want.T, got @ got.T, rtol=2e-4, atol=1e-5)
+    assert cached_ops.spmm_widths.count(ni) == 2
