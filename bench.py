@@ -375,14 +375,15 @@ def run_ours(args):
 
         def e2e_step():
             ops.clear_cache()
-            dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            g = GraphData(dv["x"], dv["y"], dv["edge_index"], dv["edge_attr"], dv["train_mask"], dv["val_mask"], dv["test_mask"])
+            # the call a user of the reference makes: host data + a device; the model moves it (src/gnngp.py:69)
+            g = GraphData(host["x"], host["y"], host["edge_index"], host["edge_attr"], host["train_mask"], host["val_mask"],
+                          host["test_mask"])
             if world == 1:
                 m = GNNGP(g, device=dev, Nystrom=True)
             else:
                 from gnngp_b200.shard import ShardedGNNGP
                 m = ShardedGNNGP(g, device=dev, Nystrom=True)
-            m.mask["landmark"] = dv["landmark"]
+            m.mask["landmark"] = host["landmark"].to(dev, non_blocking=True)
             m.set_hyper_param(args.layers, args.sigma_b, args.sigma_w, method="GCN")
             m.predict(host_nugget.to(dev, non_blocking=True))
             s = m.get_summary()

@@ -396,6 +396,19 @@ extern "C" int gnngp_panelize_peers_f32(const void *peer_ptrs_dev, int world, in
     return GNNGP_OK;
 }
 
+extern "C" int gnngp_panelize_f32(const float *B, int64_t ldb, int64_t n, int64_t k, float *panels, gnngp_stream_t stream)
+{
+    using namespace gnngp;
+    GNNGP_REQUIRE(B && panels && n > 0 && k > 0 && ldb >= k, "panelize: bad arguments");
+    GNNGP_REQUIRE(aligned(panels, 16), "panelize: the panel buffer must be 16-byte aligned");
+    const int64_t n_tiles = ceil_div(k, PANEL);
+    const int64_t quads = n_tiles * n * (PANEL / 4);
+    panelize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(quads, 256), (int64_t)sm_count() * 16), 256, 0, as_stream(stream)>>>(
+        B, ldb, n, k, n_tiles, panels, aligned(B, 16) && ldb % 4 == 0);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+
 extern "C" int gnngp_spmm_panels_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows,
                                      int64_t n_cols, int64_t nnz, const float *panels, int64_t k, float alpha, float *C,
                                      int64_t ldc, int nnz_per_warp, gnngp_stream_t stream)

@@ -12,6 +12,8 @@ come from :mod:`gnngp_b200.synth` or from any object exposing the same attribute
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -38,12 +40,83 @@ class GraphData(object):
     def to(self, device):
         if device is None:
             return self
+        device = torch.device(device)
+        if (device.type == "cuda" and os.environ.get("GNNGP_STREAM_UPLOAD", "0") == "1"
+                and self.edge_index is not None and self.edge_attr is not None
+                and not self.edge_index.is_cuda and self.edge_index.is_pinned() and self.edge_attr.is_pinned()
+                and self.edge_index.size(1) >= int(os.environ.get("GNNGP_STREAM_UPLOAD_MIN_NNZ", str(1 << 22)))):
+            return self._streamed_to(device)
         out = GraphData.__new__(GraphData)
         out.num_classes = self.num_classes
         for name in self._tensor_fields:
             value = getattr(self, name)
-            setattr(out, name, value.to(device) if value is not None else None)
+            if value is not None:                      # pinned host buffers: stream-ordered asynchronous copies
+                value = value.to(device, non_blocking=bool(not value.is_cuda and value.is_pinned()))
+            setattr(out, name, value)
         return out
+
+    def _streamed_to(self, device, chunks: int = 8):
+        """Host -> device copy of a large graph that lets the consumer start before the edge list has arrived
+        (opt-in, ``GNNGP_STREAM_UPLOAD=1``; pinned host tensors, edge list sorted by row as ``transition_matrix``
+        / ``coalesce`` leave it).  Features, labels and masks go first on a copy stream; the edge list follows
+        in ``chunks`` row-aligned pieces, each with its own event.  The returned object carries
+        ``_stream_plan`` = row bounds, nonzero bounds and events; ``GNNGP`` turns it into a row-chunked CSR
+        whose pieces are converted and multiplied as they arrive (``ops.register_streamed``)."""
+        n = self.num_nodes
+        nnz = int(self.edge_index.size(1))
+        main = torch.cuda.current_stream(device)
+        copy = _copy_stream(device)
+        row_bounds = [(n * c) // chunks for c in range(chunks + 1)]
+        inner = torch.tensor(row_bounds[1:-1], dtype=self.edge_index.dtype)
+        cuts = torch.searchsorted(self.edge_index[0].contiguous(), inner).tolist()     # host binary searches
+        nnz_bounds = [0]
+        for c in cuts:                                     # monotone even if the list turns out NOT to be sorted:
+            nnz_bounds.append(max(nnz_bounds[-1], int(c)))  # the pieces always tile [0, nnz) so every edge is copied
+        nnz_bounds.append(nnz)
+        out = GraphData.__new__(GraphData)
+        out.num_classes = self.num_classes
+        small = {}
+        for name in self._tensor_fields:
+            value = getattr(self, name)
+            if name in ("edge_index", "edge_attr") or value is None:
+                continue
+            small[name] = torch.empty(value.shape, dtype=value.dtype, device=device)
+        edge_index = torch.empty((2, nnz), dtype=self.edge_index.dtype, device=device)
+        edge_attr = torch.empty((nnz,), dtype=self.edge_attr.dtype, device=device)
+        copy.wait_stream(main)                             # the buffers above are safe to write from here on
+        events = []
+        with torch.cuda.stream(copy):
+            for name, dst in small.items():
+                dst.copy_(getattr(self, name), non_blocking=True)
+            ready_small = torch.cuda.Event()
+            ready_small.record(copy)
+            for c in range(chunks):
+                a, b = nnz_bounds[c], nnz_bounds[c + 1]
+                if b > a:
+                    edge_index[0, a:b].copy_(self.edge_index[0, a:b], non_blocking=True)
+                    edge_index[1, a:b].copy_(self.edge_index[1, a:b], non_blocking=True)
+                    edge_attr[a:b].copy_(self.edge_attr[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                events.append(ev)
+        for t in list(small.values()) + [edge_index, edge_attr]:
+            t.record_stream(copy)
+        main.wait_event(ready_small)                       # features / labels / masks: needed first, small
+        for name in self._tensor_fields:
+            setattr(out, name, small.get(name))
+        out.edge_index, out.edge_attr = edge_index, edge_attr
+        out._stream_plan = {"row_bounds": row_bounds, "nnz_bounds": nnz_bounds, "events": events, "all": events[-1]}
+        return out
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
 
 
 def coalesce_edges(edge_index: torch.Tensor, edge_weight: torch.Tensor, num_nodes: int):

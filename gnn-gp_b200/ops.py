@@ -32,6 +32,28 @@ class CsrMatrix(object):
         self.nnz = int(colidx.numel())
 
 
+class ChunkedCsr(object):
+    """The adjacency as consecutive row blocks, each a :class:`CsrMatrix` over all columns (``row_offset`` =
+    first row).  Built by ``CudaOps.register_streamed`` from an edge list that is still arriving from the host:
+    every block is converted — and can be multiplied — as soon as ITS edges are on the device."""
+
+    def __init__(self, n_rows: int, n_cols: int, blocks, in_range: torch.Tensor):
+        self.n_rows, self.n_cols, self.blocks, self.row_offset = int(n_rows), int(n_cols), list(blocks), 0
+        self.nnz = sum(b.nnz for b in self.blocks)
+        self.in_range = in_range          # device flag: every edge of every block lies inside the block's row range
+
+    def merged(self) -> CsrMatrix:
+        """One CsrMatrix over all rows (concatenation; the blocks are consecutive and internally sorted)."""
+        offs, total = [], 0
+        for b in self.blocks:
+            offs.append(total)
+            total += b.nnz
+        rowptr = torch.cat([b.rowptr[:-1] + o for b, o in zip(self.blocks, offs)] +
+                           [torch.tensor([total], dtype=torch.int64, device=self.blocks[0].rowptr.device)])
+        return CsrMatrix(rowptr, torch.cat([b.colidx for b in self.blocks]), torch.cat([b.vals for b in self.blocks]),
+                         self.n_rows, self.n_cols, 0)
+
+
 class CudaOps(object):
     name = "cuda-sm100a"
 
@@ -140,7 +162,7 @@ class CudaOps(object):
 
     def csr_of(self, A: torch.Tensor) -> CsrMatrix:
         """CSR of a torch sparse COO adjacency, converted once and cached on the tensor's storage."""
-        if isinstance(A, CsrMatrix):
+        if isinstance(A, (CsrMatrix, ChunkedCsr)):
             return A
         if not A.is_sparse:
             raise RuntimeError("gnngp_b200: adjacency must be a torch sparse COO tensor")
@@ -161,9 +183,63 @@ class CudaOps(object):
     def clear_cache(self) -> None:
         self._csr_cache.clear()
 
+    def register_streamed(self, A: torch.Tensor, plan: dict) -> ChunkedCsr:
+        """Row-chunked CSR of an adjacency whose edge list is being uploaded in row-aligned pieces
+        (``datasets.GraphData._streamed_to``): for every piece the current stream waits for that piece's copy
+        event and converts it, so conversion and the first sparse product overlap with the rest of the upload.
+        The result is cached like ``csr_of``'s, so every later ``csr_of(A)`` returns it."""
+        idx, val = A._indices(), A._values()
+        n = int(A.shape[0])
+        main = torch.cuda.current_stream(idx.device)
+        blocks = []
+        in_range = torch.ones((), dtype=torch.bool, device=idx.device)
+        rb, nb = plan["row_bounds"], plan["nnz_bounds"]
+        for c, event in enumerate(plan["events"]):
+            main.wait_event(event)
+            a, b = nb[c], nb[c + 1]
+            r0, r1 = rb[c], rb[c + 1]
+            rows = idx[0, a:b]
+            if b > a:
+                in_range = in_range & (rows.min() >= r0) & (rows.max() < r1)
+            block = self.csr_from_coo(rows - r0, idx[1, a:b], val[a:b] if val.dtype == torch.float32 else val[a:b].float(),
+                                      max(r1 - r0, 1), int(A.shape[1]), r0)
+            block.n_rows = r1 - r0
+            blocks.append(block)
+        chunked = ChunkedCsr(n, int(A.shape[1]), blocks, in_range)
+        key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index)
+        if len(self._csr_cache) >= 2:
+            self._csr_cache.clear()
+        self._csr_cache[key] = (chunked, idx, val)
+        return chunked
+
+    def _spmm_chunked(self, csr: ChunkedCsr, B: torch.Tensor, alpha: float, out: Optional[torch.Tensor]) -> torch.Tensor:
+        B, ldb = self._mat(B, "B")
+        if B.shape[0] != csr.n_cols:
+            raise RuntimeError("spmm: B has %d rows, adjacency has %d columns" % (B.shape[0], csr.n_cols))
+        k = B.shape[1]
+        if out is None:
+            out = self.empty(csr.n_rows, k, B.device)
+        if out.shape != (csr.n_rows, k) or (k > 1 and out.stride(1) != 1):
+            raise RuntimeError("spmm: out must be a [%d x %d] row-major view" % (csr.n_rows, k))
+        if int(self.spmm_tile_cols) == 0 and csr.nnz >= 64 * csr.n_rows and k >= 256:
+            need = self.lib.query("gnngp_spmm_workspace_bytes", csr.n_cols, k)
+            ws = self.workspace(need + 256, B.device, "spmm")
+            panels = (ws.data_ptr() + 255) // 256 * 256
+            self.lib.call("gnngp_panelize_f32", B.data_ptr(), ldb, B.shape[0], k, panels, self._stream())   # once for all blocks
+            for blk in csr.blocks:
+                if blk.n_rows > 0:
+                    self.spmm_panels(blk, panels, k, alpha, out[blk.row_offset:blk.row_offset + blk.n_rows])
+        else:
+            for blk in csr.blocks:
+                if blk.n_rows > 0:
+                    self.spmm(blk, B, alpha, out=out[blk.row_offset:blk.row_offset + blk.n_rows])
+        return out
+
     def restrict_columns(self, csr: CsrMatrix, cols: torch.Tensor) -> CsrMatrix:
         """CSR of ``A[:, cols]`` with column ids renumbered to positions in ``cols`` (one pass over the
         nonzeros with torch index ops; done once per landmark set)."""
+        if isinstance(csr, ChunkedCsr):
+            csr = csr.merged()
         dev = csr.colidx.device
         lookup = torch.full((csr.n_cols,), -1, dtype=torch.int32, device=dev)
         lookup[cols] = torch.arange(cols.numel(), dtype=torch.int32, device=dev)
@@ -177,6 +253,8 @@ class CudaOps(object):
 
     # ------------------------------------------------------------------ K1 SpMM
     def spmm(self, csr: CsrMatrix, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if isinstance(csr, ChunkedCsr):
+            return self._spmm_chunked(csr, B, alpha, out)
         B, ldb = self._mat(B, "B")
         if B.shape[0] != csr.n_cols:
             raise RuntimeError("spmm: B has %d rows, adjacency has %d columns" % (B.shape[0], csr.n_cols))

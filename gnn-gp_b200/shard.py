@@ -133,6 +133,9 @@ class ShardedGNNGP(object):
         self.device = device
         self.set_hyper_param(L, sigma_b, sigma_w, Nystrom, initial, method, **params)
         graph = data.to(device)
+        plan = getattr(graph, "_stream_plan", None)
+        if plan is not None:                                # streamed upload: this path reads the whole edge list at once
+            torch.cuda.current_stream(graph.edge_index.device).wait_event(plan["all"])
         self.N, self.X, self.y, self.A, self.mask = datasets.get_data(graph)
         self.layout = RowLayout(self.N, self.comm.world, self.comm.rank)
         lay = self.layout

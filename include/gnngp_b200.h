@@ -79,6 +79,9 @@ int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float
  * Together they replace "NCCL all-gather of the factor rows, then A_r @ X" (SURVEY.md section 8e). */
 int gnngp_panelize_peers_f32(const void *peer_ptrs_dev, int world, int64_t rows_per_rank, int64_t ld, int64_t n,
                              int64_t k, float *panels, gnngp_stream_t stream);
+/* The panel copy on its own (local operand B: [n x k] ld ldb, any alignment), for callers that run several
+ * products — e.g. the row blocks of a graph that is still being uploaded — against one operand. */
+int gnngp_panelize_f32(const float *B, int64_t ldb, int64_t n, int64_t k, float *panels, gnngp_stream_t stream);
 int gnngp_spmm_panels_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows,
                           int64_t n_cols, int64_t nnz, const float *panels, int64_t k, float alpha, float *C,
                           int64_t ldc, int nnz_per_warp, gnngp_stream_t stream);

@@ -107,6 +107,48 @@ def test_reuse_products_across_a_sweep_matches_fresh_models():
     assert "first" in sweep._product_cache
 
 
+@pytest.mark.parametrize("shuffled", [False, True])
+def test_streamed_upload_matches_plain_upload(monkeypatch, shuffled):
+    """Opt-in streamed host->device upload (row-chunked CSR built and multiplied while the edge list arrives):
+    same kernel and metrics as the plain upload; an edge list that is NOT sorted by row is detected on the
+    device and recomputed from a plain CSR (with a warning)."""
+    import warnings
+    from gnngp_b200.datasets import GraphData
+    from gnngp_b200.gnngp import GNNGP
+    from gnngp_b200.ops import ChunkedCsr, default_ops
+    dev = torch.device("cuda:0")
+    case = cases.CASES["pubmed-GCN-nys4-L2"]
+    data, masks, nugget = cases.build_inputs(case)
+    edge_index, edge_attr = data.edge_index, data.edge_attr
+    if shuffled:
+        perm = torch.randperm(edge_index.size(1), generator=torch.Generator().manual_seed(3))
+        edge_index, edge_attr = edge_index[:, perm].contiguous(), edge_attr[perm].contiguous()
+
+    def run(stream):
+        monkeypatch.setenv("GNNGP_STREAM_UPLOAD", "1" if stream else "0")
+        monkeypatch.setenv("GNNGP_STREAM_UPLOAD_MIN_NNZ", "1")
+        default_ops().clear_cache()
+        host = GraphData(data.x.pin_memory(), data.y.pin_memory(), edge_index.pin_memory(), edge_attr.pin_memory(),
+                         data.train_mask.pin_memory(), data.val_mask.pin_memory(), data.test_mask.pin_memory())
+        model = GNNGP(host, device=dev, Nystrom=True)
+        was_chunked = isinstance(default_ops().csr_of(model.A), ChunkedCsr)
+        model.mask["landmark"] = masks["landmark"].to(dev)
+        model.set_hyper_param(case["L"], case["sigma_b"], case["sigma_w"], method="GCN")
+        model.predict(nugget.to(dev))
+        return model, was_chunked
+
+    plain, chunked_plain = run(False)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        streamed, chunked_streamed = run(True)
+    assert not chunked_plain and chunked_streamed
+    assert any("not sorted by row" in str(w.message) for w in caught) == shuffled
+    a, b = streamed.Q[:400].double(), plain.Q[:400].double()
+    assert float((a @ a.T - b @ b.T).norm() / (b @ b.T).norm()) < 1e-5
+    for key in ("train", "val", "test"):
+        assert float((streamed.result[key] - plain.result[key]).abs().max()) < 0.02
+
+
 def test_zz_write_parity_report():
     """Collect the measured parity errors (committed under profiles/ by the builder)."""
     os.makedirs("gpurun_out", exist_ok=True)
