@@ -46,6 +46,7 @@ class ChunkedCsr(object):
         """One CsrMatrix over all rows (concatenation; the blocks are consecutive and internally sorted)."""
         offs, total = [], 0
         for b in self.blocks:
+            torch.cuda.current_stream(b.rowptr.device).wait_event(b.ready)
             offs.append(total)
             total += b.nnz
         rowptr = torch.cat([b.rowptr[:-1] + o for b, o in zip(self.blocks, offs)] +
@@ -190,21 +191,36 @@ class CudaOps(object):
         The result is cached like ``csr_of``'s, so every later ``csr_of(A)`` returns it."""
         idx, val = A._indices(), A._values()
         n = int(A.shape[0])
-        main = torch.cuda.current_stream(idx.device)
+        dev = idx.device
+        main = torch.cuda.current_stream(dev)
+        convert = self._convert_stream(dev)
+        convert.wait_stream(main)
         blocks = []
-        in_range = torch.ones((), dtype=torch.bool, device=idx.device)
         rb, nb = plan["row_bounds"], plan["nnz_bounds"]
-        for c, event in enumerate(plan["events"]):
-            main.wait_event(event)
-            a, b = nb[c], nb[c + 1]
-            r0, r1 = rb[c], rb[c + 1]
-            rows = idx[0, a:b]
-            if b > a:
-                in_range = in_range & (rows.min() >= r0) & (rows.max() < r1)
-            block = self.csr_from_coo(rows - r0, idx[1, a:b], val[a:b] if val.dtype == torch.float32 else val[a:b].float(),
-                                      max(r1 - r0, 1), int(A.shape[1]), r0)
-            block.n_rows = r1 - r0
-            blocks.append(block)
+        # conversions run on their own stream, each after ITS piece's copy event, and leave a `ready` event per
+        # block: the main stream only waits for a block right before it multiplies with it (_spmm_chunked), so the
+        # product over block c overlaps with the upload and conversion of blocks c+1, c+2, ...
+        with torch.cuda.stream(convert):
+            in_range = torch.ones((), dtype=torch.bool, device=dev)
+            for c, event in enumerate(plan["events"]):
+                convert.wait_event(event)
+                a, b = nb[c], nb[c + 1]
+                r0, r1 = rb[c], rb[c + 1]
+                rows = idx[0, a:b]
+                if b > a:
+                    in_range = in_range & (rows.min() >= r0) & (rows.max() < r1)
+                # clamped so that the piece is a well-formed CSR even if the list is NOT sorted by row (the flag above
+                # then makes the caller recompute from a plain CSR; the clamped block is never trusted)
+                local = (rows - r0).clamp_(0, max(r1 - r0 - 1, 0))
+                block = self.csr_from_coo(local, idx[1, a:b], val[a:b] if val.dtype == torch.float32 else val[a:b].float(),
+                                          max(r1 - r0, 1), int(A.shape[1]), r0)
+                block.n_rows = r1 - r0
+                for t in (block.rowptr, block.colidx, block.vals):
+                    t.record_stream(main)
+                block.ready = torch.cuda.Event()
+                block.ready.record(convert)
+                blocks.append(block)
+            in_range.record_stream(main)
         chunked = ChunkedCsr(n, int(A.shape[1]), blocks, in_range)
         key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index)
         if len(self._csr_cache) >= 2:
@@ -212,8 +228,17 @@ class CudaOps(object):
         self._csr_cache[key] = (chunked, idx, val)
         return chunked
 
+    def _convert_stream(self, device):
+        key = (device.index, "convert-stream")
+        stream = self._workspace.get(key)
+        if stream is None:
+            stream = torch.cuda.Stream(device=device)
+            self._workspace[key] = stream
+        return stream
+
     def _spmm_chunked(self, csr: ChunkedCsr, B: torch.Tensor, alpha: float, out: Optional[torch.Tensor]) -> torch.Tensor:
         B, ldb = self._mat(B, "B")
+        main = torch.cuda.current_stream(B.device)
         if B.shape[0] != csr.n_cols:
             raise RuntimeError("spmm: B has %d rows, adjacency has %d columns" % (B.shape[0], csr.n_cols))
         k = B.shape[1]
@@ -227,10 +252,12 @@ class CudaOps(object):
             panels = (ws.data_ptr() + 255) // 256 * 256
             self.lib.call("gnngp_panelize_f32", B.data_ptr(), ldb, B.shape[0], k, panels, self._stream())   # once for all blocks
             for blk in csr.blocks:
+                main.wait_event(blk.ready)
                 if blk.n_rows > 0:
                     self.spmm_panels(blk, panels, k, alpha, out[blk.row_offset:blk.row_offset + blk.n_rows])
         else:
             for blk in csr.blocks:
+                main.wait_event(blk.ready)
                 if blk.n_rows > 0:
                     self.spmm(blk, B, alpha, out=out[blk.row_offset:blk.row_offset + blk.n_rows])
         return out
