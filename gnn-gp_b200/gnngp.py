@@ -71,8 +71,26 @@ class GNNGP(object):
         """``Q`` (Nystrom) or ``K`` (exact); memoised until the next ``set_hyper_param``
         (reference ``src/gnngp.py:87-99``)."""
         if not self.computed:
-            self._compute_kernel()
+            if self._streamed is None:
+                self._compute_kernel()
+            else:
+                self._compute_kernel_streamed()
         return self.Q if self.Nystrom else self.K
+
+    def _compute_kernel_streamed(self) -> None:
+        """First kernel after a streamed upload: the row-chunked CSR is only valid if the host edge list was
+        sorted by row.  The device-side check is read AFTER the recursion has been enqueued (reading it first
+        would stall the host until the upload ends and forfeit the overlap); an unsorted list gives a well-formed
+        but wrong CSR (possibly NaNs, which the eigensolver rejects), so a failure is treated like a failed check."""
+        try:
+            self._compute_kernel()
+        except Exception:
+            if self._streamed_edges_ok():
+                raise
+            self._compute_kernel()
+            return
+        if not self._streamed_edges_ok():
+            self._compute_kernel()                           # recomputed from a plain CSR
 
     def predict(self, nugget: Union[float, Tensor] = 1e-2):
         """Posterior means for every nugget, then the per-mask metrics (reference ``src/gnngp.py:101-124``).
@@ -86,8 +104,6 @@ class GNNGP(object):
         per_nugget = self.fit if len(grid) > 1 else self.fit.unsqueeze(0)
         self.result = predict.result(per_nugget, self.y, self.mask)
         self.nugget = grid
-        if self._streamed is not None and not self._streamed_edges_ok():
-            return self.predict(nugget)                      # recomputed from a plain CSR
         return self.fit
 
     def _streamed_edges_ok(self) -> bool:
@@ -95,6 +111,7 @@ class GNNGP(object):
         checked that on the device.  If it was not, drop the chunked CSR (``csr_of`` then converts the complete
         edge list the ordinary way) and report it so that the caller recomputes."""
         chunked, self._streamed = self._streamed, None
+        torch.cuda.current_stream(chunked.in_range.device).wait_event(chunked.blocks[-1].ready)
         if bool(chunked.in_range.item()):
             return True
         import warnings
