@@ -66,13 +66,7 @@ class GraphData(object):
         nnz = int(self.edge_index.size(1))
         main = torch.cuda.current_stream(device)
         copy = _copy_stream(device)
-        row_bounds = [(n * c) // chunks for c in range(chunks + 1)]
-        inner = torch.tensor(row_bounds[1:-1], dtype=self.edge_index.dtype)
-        cuts = torch.searchsorted(self.edge_index[0].contiguous(), inner).tolist()     # host binary searches
-        nnz_bounds = [0]
-        for c in cuts:                                     # monotone even if the list turns out NOT to be sorted:
-            nnz_bounds.append(max(nnz_bounds[-1], int(c)))  # the pieces always tile [0, nnz) so every edge is copied
-        nnz_bounds.append(nnz)
+        row_bounds, nnz_bounds = chunk_bounds(self.edge_index[0], n, chunks)
         out = GraphData.__new__(GraphData)
         out.num_classes = self.num_classes
         small = {}
@@ -107,6 +101,22 @@ class GraphData(object):
         out.edge_index, out.edge_attr = edge_index, edge_attr
         out._stream_plan = {"row_bounds": row_bounds, "nnz_bounds": nnz_bounds, "events": events, "all": events[-1]}
         return out
+
+
+def chunk_bounds(rows: torch.Tensor, n: int, chunks: int):
+    """Row-aligned pieces of a row-sorted edge list: ``row_bounds[c] .. row_bounds[c+1]`` are the rows of piece
+    c and ``nnz_bounds[c] .. nnz_bounds[c+1]`` its edges (binary searches on the HOST copy of the row ids).
+    The edge ranges are monotone and tile ``[0, nnz)`` even when the list is NOT sorted — every edge is copied
+    exactly once and the device-side range check then reports the misplaced ones."""
+    nnz = int(rows.numel())
+    row_bounds = [(n * c) // chunks for c in range(chunks + 1)]
+    inner = torch.tensor(row_bounds[1:-1], dtype=rows.dtype)
+    cuts = torch.searchsorted(rows.contiguous(), inner).tolist()
+    nnz_bounds = [0]
+    for c in cuts:
+        nnz_bounds.append(min(nnz, max(nnz_bounds[-1], int(c))))
+    nnz_bounds.append(nnz)
+    return row_bounds, nnz_bounds
 
 
 _COPY_STREAMS = {}

@@ -51,3 +51,28 @@ def test_hyper_param_contract():
     assert (model.L, model.sigma_b, model.method, model.params, model.computed) == (2, 0.5, "SAGE", {}, False)
     summary = model.get_summary()
     assert set(summary) == {"L", "sigma_b", "sigma_w", "Nystrom", "initial", "method"}
+
+
+def test_streamed_upload_chunk_bounds_tile_the_edge_list():
+    """Host logic of the streamed upload: row-aligned pieces of a row-sorted list; monotone tiling of [0, nnz)
+    even for an unsorted list (so that every edge is always copied exactly once)."""
+    import torch
+    from gnngp_b200.datasets import chunk_bounds
+    g = torch.Generator().manual_seed(0)
+    n, nnz = 1000, 20000
+    rows = torch.sort(torch.randint(0, n, (nnz,), generator=g)).values
+    rb, nb = chunk_bounds(rows, n, 8)
+    assert rb[0] == 0 and rb[-1] == n and nb[0] == 0 and nb[-1] == nnz and len(rb) == len(nb) == 9
+    for c in range(8):
+        piece = rows[nb[c]:nb[c + 1]]
+        assert nb[c] <= nb[c + 1]
+        if piece.numel():
+            assert int(piece.min()) >= rb[c] and int(piece.max()) < rb[c + 1]
+    shuffled = rows[torch.randperm(nnz, generator=g)]
+    rb, nb = chunk_bounds(shuffled, n, 8)
+    assert nb[0] == 0 and nb[-1] == nnz and all(a <= b for a, b in zip(nb, nb[1:]))
+    # degenerate shapes: fewer rows than pieces, empty list
+    rb, nb = chunk_bounds(torch.tensor([0, 0, 1, 2]), 3, 8)
+    assert nb[0] == 0 and nb[-1] == 4 and all(a <= b for a, b in zip(nb, nb[1:]))
+    rb, nb = chunk_bounds(torch.zeros(0, dtype=torch.int64), 5, 4)
+    assert nb == [0, 0, 0, 0, 0]
