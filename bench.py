@@ -1,18 +1,28 @@
 #!/usr/bin/env python
 """bench.py — GCNGP-X fit+predict seconds on a synthetic Reddit-shape graph (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--shape reddit] [--fraction 50] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--shape reddit] [--fraction 10] [--impl reference]
 
 One "step" = what the reference times per run (``src/main.py:109-116``, landmark draw injected):
 ``set_hyper_param`` + ``predict`` (kernel recursion, fit for 101 nuggets, metrics) + ``get_summary``.
+Default workload = the north-star point: Reddit shape, GCN, L = 2, fraction 10 (15 404 landmarks); the
+fraction-50 point of the sweep (figure4.sh:2) is measured too and reported under ``sweep``.
 
 ``value``   seconds per step with the graph resident in HBM (CSR built once, like the model object the
             reference keeps across runs), CUDA events, max over ranks, K steps after W warm-ups.
 ``e2e``     seconds per step through the public ``GNNGP`` API from pinned HOST buffers: host→device copy
             of features / labels / edges / masks, model construction (COO→CSR), predict, summary on host.
-``roofline``the dominant kernel (layer-2 CSR SpMM): algorithmic bytes ÷ its CUDA-event time.
-``cpu_baseline`` the oracle port of the reference algorithm on the host cores, on a bounded row sample.
+``roofline``the dominant kernel of this library (layer-2 CSR SpMM): algorithmic work ÷ its
+            CUDA-event time, against the binding peak of ``max(bytes / HBM, flops / fp32-FMA)``.
+``config.parity_vs_reference``  the timed run's outputs against the UNMODIFIED reference: live against the
+            reference's own torch path on this GPU (``gpu_reference``) at the headline fraction, and against the
+            golden fixture ``tests/golden/big/reddit-GCN-nys50-L2.npz`` (reference CPU run) at fraction 50.
+``gpu_reference``  the unmodified reference (``baseline/_ref``) on CUDA tensors on the same B200, same inputs.
+``cpu_baseline``   the unmodified reference's functions on the host cores on a bounded row sample (estimate).
 ``--impl reference`` prints the CPU arm alone (rank 0 only under torchrun).
+
+The graph is generated on the HOST (seeded, deterministic) so that it is exactly the graph the golden fixture
+was made from; under torchrun rank 0 generates it and broadcasts it.
 
 N > 1 (torchrun, one rank per GPU): adjacency and factor are row-sharded, each layer all-gathers the
 factor rows over NCCL and the fit all-reduces ``Q_bᵀQ_b`` (gnngp_b200/shard.py); total work is fixed →
@@ -30,11 +40,14 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "gcngp_x_fit_predict_seconds"
 UNIT = "s"
+GOLDEN_F50 = "reddit-GCN-nys50-L2"
 
 
 def parse_args():
@@ -44,29 +57,26 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="reddit")
-    ap.add_argument("--fraction", type=int, default=50)
+    ap.add_argument("--fraction", type=int, default=10)
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--sigma_b", type=float, default=0.0)
     ap.add_argument("--sigma_w", type=float, default=1.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--stream-upload", default="auto", choices=["auto", "0", "1"],
-                    help="e2e leg: let the model upload the pinned edge list in pieces and start on them as they arrive "
-                         "(GNNGP_STREAM_UPLOAD); auto = the measured best for this N")
-    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="adjacency rows in the CPU sample (0 = auto)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the fraction-50 point and its golden parity check")
+    ap.add_argument("--stream-upload", default="0", choices=["0", "1"],
+                    help="e2e leg: GNNGP_STREAM_UPLOAD (opt-in piecewise upload of the pinned edge list); default = the "
+                         "library's default configuration (off)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = all cores)")
     ap.add_argument("--breakdown", default="", help="write the per-operator timing table to this JSON file")
     return ap.parse_args()
 
 
-# e2e leg: streamed upload per world size ("1" only where an A/B on the B200 box showed a gain)
-# N = 1: 0.3200 s vs 0.3325 s (profiles/r1/call30_bench_reddit_f50_n1_*_upload.json); N > 1 not measured yet
-STREAM_UPLOAD_AUTO = {1: "1"}
-
-
-def workload_name(args) -> str:
+def workload_name(args, fraction=None) -> str:
     return "GCNGP-X (GCN, L=%d, fraction=%d, sigma_b=%g, sigma_w=%g, 101 nuggets) on synthetic %s-shape graph" % (
-        args.layers, args.fraction, args.sigma_b, args.sigma_w, args.shape)
+        args.layers, fraction or args.fraction, args.sigma_b, args.sigma_w, args.shape)
 
 
 # --------------------------------------------------------------------------------------------
@@ -117,105 +127,122 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm (oracle port on a bounded sample)
+# inputs
 # --------------------------------------------------------------------------------------------
-def cpu_sampled_baseline(args, data=None, land_mask=None) -> dict:
-    """Time the reference algorithm's stages on host cores on a row sample and scale to full size."""
-    import numpy as np
-    from oracle import sampled
-    from oracle import gnngp_oracle as orc
+def host_graph(args):
+    """The seeded synthetic graph, generated on the host: the same tensors on every machine (this is the graph
+    the golden fixtures of tests/golden/big were computed from; checked through the input checksum)."""
     from gnngp_b200 import synth
-    spec = synth.SHAPES[args.shape]
-    n, f, c = spec["n"], spec["f"], max(spec["c"], 1)
-    n_train = spec["split"][0]
-    if data is None:
-        # no GPU data at hand (--impl reference): generate a graph of the same shape on the host.  For the
-        # Reddit shape that is ~115 M edges; the sample only needs `rows` adjacency rows, so a graph with the
-        # same degree law restricted to the sampled rows is drawn instead (same nnz per row in expectation).
-        data, land_mask = host_sample_graph(args, spec)
-    rows_wanted = args.cpu_sample_rows or max(256, min(n, int(n * 3.2e7 / max(1, data["nnz_total"]))))
-    rng = np.random.default_rng(args.seed)
-    pick = np.sort(rng.choice(n, size=min(rows_wanted, n), replace=False))
-    indptr, indices, vals = data["rows_csr"](pick)
-    sample = sampled.RowSample(indptr, indices, vals, n)
-    x = data["x"]
-    land_idx = np.nonzero(land_mask)[0]
-    n_land = int(land_idx.shape[0])
-    dense_rows = int(min(n, max(4096, min(65536, n // 4))))
-    threads = orc._native().oracle_num_threads() if orc._native() is not None else 1
-    est = sampled.estimate_gcn_nystrom_seconds(sample, n, x, x[land_idx] if n_land >= f else np.zeros((n_land, f), np.float32),
-                                               n_land, n_train, c, 101, args.layers, args.sigma_b, args.sigma_w,
-                                               dense_rows, seed=args.seed)
-    return {"value": est["total_estimated_s"], "unit": UNIT, "cores": int(max(threads, os.cpu_count() or 1)),
-            "kind": "port",
-            "sample": "%d of %d adjacency rows for the two sparse products, %d rows for the dense row-separable stages, "
-                      "both eigendecompositions (n=%d, %d) at full size; stage times scaled by the inverse sampling rate; "
-                      "measured %.1f s of CPU work" % (sample.n_rows, n, dense_rows, n_land, n_land + 1, est["sample_measured_s"]),
-            "stages_s": {k: round(v, 4) for k, v in est.items()}}
+    return synth.make_graph(args.shape, seed=args.seed, device=None, normalization="sym")
 
 
-def host_sample_graph(args, spec):
-    """Host-only stand-in used by --impl reference: features and a landmark mask of the right shape, and
-    adjacency rows drawn with the generator's degree law for the sampled nodes only."""
-    import numpy as np
-    n, f = spec["n"], spec["f"]
-    rng = np.random.default_rng(args.seed + 1)
-    x = rng.standard_normal((n, f), dtype=np.float32)
-    train = np.zeros(n, dtype=bool)
-    train[rng.choice(n, spec["split"][0], replace=False)] = True
-    land = train & (rng.random(n) < 1.0 / args.fraction)
-    nnz_total = 2 * spec["und"] + n
-    weights = np.arange(1, n + 1, dtype=np.float64) ** -0.7
-    perm = rng.permutation(n)
-    share = np.empty(n)
-    share[perm] = weights / weights.sum()           # expected share of edge endpoints per node
-
-    def rows_csr(pick):
-        deg = np.maximum(1, rng.poisson(share[pick] * 2 * spec["und"]) + 1)
-        indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
-        cdf = np.cumsum(share)
-        indices = np.searchsorted(cdf, rng.random(int(indptr[-1]))).clip(max=n - 1).astype(np.int32)
-        for i in range(len(pick)):                   # column order inside a row, as in a coalesced operand
-            indices[indptr[i]:indptr[i + 1]].sort()
-        vals = (rng.random(int(indptr[-1]), dtype=np.float32) + 0.5) / np.float32(500.0)
-        return indptr, indices, vals
-
-    return {"x": x, "rows_csr": rows_csr, "nnz_total": nnz_total}, land
+def device_graph(args, dev, world: int, rank: int):
+    """The graph on this rank's GPU.  One rank generates (host, ~25 s at the Reddit shape) and broadcasts."""
+    import torch.distributed as dist
+    from gnngp_b200.datasets import GraphData
+    fields = ("x", "y", "edge_index", "edge_attr", "train_mask", "val_mask", "test_mask")
+    if world == 1:
+        host = host_graph(args)
+        return host.to(dev), host
+    meta = [None]
+    host = None
+    if rank == 0:
+        host = host_graph(args)
+        meta = [{k: (tuple(getattr(host, k).shape), getattr(host, k).dtype) for k in fields} | {"c": host.num_classes}]
+    dist.broadcast_object_list(meta, src=0)
+    tensors = {}
+    for k in fields:
+        shape, dtype = meta[0][k]
+        t = getattr(host, k).to(dev) if rank == 0 else torch.empty(shape, dtype=torch.uint8 if dtype == torch.bool else dtype, device=dev)
+        if dtype == torch.bool:
+            t = t.to(torch.uint8)
+        dist.broadcast(t, src=0)
+        tensors[k] = t.to(torch.bool) if dtype == torch.bool else t
+    return GraphData(tensors["x"], tensors["y"], tensors["edge_index"], tensors["edge_attr"], tensors["train_mask"],
+                     tensors["val_mask"], tensors["test_mask"], num_classes=meta[0]["c"]), host
 
 
-def device_graph_for_cpu(model_data, csr):
-    """Adapter: hand the CPU arm the SAME graph the GPU arm ran on (rows sampled from the device CSR)."""
-    import numpy as np
-    rowptr = csr.rowptr.cpu().numpy()
-    x = model_data.x.detach().cpu().numpy()
+# --------------------------------------------------------------------------------------------
+# parity of a finished run against reference outputs (golden fixture or live reference run)
+# --------------------------------------------------------------------------------------------
+def rel_fro(a, b) -> float:
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
-    def rows_csr(pick):
-        starts, ends = rowptr[pick], rowptr[pick + 1]
-        deg = ends - starts
-        indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
-        pos = torch.from_numpy(np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]).astype(np.int64)).to(csr.colidx.device)
-        return indptr, csr.colidx[pos].cpu().numpy(), csr.vals[pos].cpu().numpy()
 
-    return {"x": x, "rows_csr": rows_csr, "nnz_total": int(csr.nnz)}
+def collect_samples(model, sample_idx, row_idx, best=None) -> dict:
+    """Small samples of a finished single-GPU run: Q Qᵀ block, posterior-mean rows, all argmax predictions, curves."""
+    q = model.Q[sample_idx].double()
+    curves = {k: v.numpy() for k, v in model.result.items()}
+    if best is None:
+        best = int(np.argmax(curves["val"]))
+    fit = model.fit
+    return {"ksamp": (q @ q.T).cpu().numpy(), "best": best, "fit_best": fit[best][row_idx].cpu().numpy(),
+            "fit_mid": fit[50][row_idx].cpu().numpy(), "pred_best": torch.argmax(fit[best], 1).cpu().numpy(), "curves": curves}
+
+
+def parity_record(ours: dict, ref: dict, source: str) -> dict:
+    """qqT_rel / fit_rel / argmax_flips of ``ours`` against reference samples (same sample indices, same nugget).
+    A flip counts as "clear" when the reference's own top-2 margin at that node exceeds 1e-3 of its largest
+    posterior mean (near-ties flip between any two fp32 evaluations, the reference's fp64 run included)."""
+    flips = ours["pred_best"].astype(np.int64) != np.asarray(ref["pred_best"]).astype(np.int64)
+    rec = {"source": source, "nugget_index": int(ref["best"]),
+           "qqT_rel": rel_fro(ours["ksamp"], ref["ksamp"]),
+           "fit_rel": rel_fro(ours["fit_best"], ref["fit_best"]), "fit_rel_nugget_0.1": rel_fro(ours["fit_mid"], ref["fit_mid"]),
+           "argmax_flips": int(flips.sum()), "argmax_nodes": int(flips.size)}
+    if "margin_best" in ref:
+        scale = float(ref.get("fit_scale", np.abs(ref["fit_best"]).max()))
+        rec["argmax_flips_clear_margin"] = int((flips & (np.asarray(ref["margin_best"]) > 1e-3 * scale)).sum())
+    curves = ref.get("curves") or {k: ref["result_" + k] for k in ("train", "val", "test")}
+    rec["curve_max_abs_diff"] = float(max(np.abs(ours["curves"][k] - np.asarray(curves[k])).max() for k in ("train", "val", "test")))
+    rec["ok"] = bool(rec["qqT_rel"] <= 1e-4 and rec["fit_rel_nugget_0.1"] <= 1e-3 and rec.get("argmax_flips_clear_margin", 0) == 0
+                     and rec["curve_max_abs_diff"] <= 2e-3)
+    for k in ("qqT_rel", "fit_rel", "fit_rel_nugget_0.1", "curve_max_abs_diff"):
+        rec[k] = float("%.3e" % rec[k])
+    return rec
+
+
+def load_big_golden(name: str):
+    path = os.path.join(ROOT, "tests", "golden", "big", name + ".npz")
+    return dict(np.load(path)) if os.path.exists(path) else None
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the unmodified reference's functions on a bounded sample (baseline/ref_arm.py)
+# --------------------------------------------------------------------------------------------
+def cpu_arm(args, host, land_host) -> dict:
+    from baseline import ref_arm
+    from gnngp_b200 import synth
+    rec = ref_arm.cpu_reference_sampled(host, land_host, synth.nugget_grid(), args.layers, args.sigma_b, args.sigma_w,
+                                        seed=args.seed, threads=args.cpu_threads)
+    full = ref_arm.golden_full_run_record("reddit-GCN-nys%d-L%d" % (args.fraction, args.layers)) if args.shape == "reddit" else None
+    if full is not None:
+        rec["measured_full_run"] = full
+    return rec
 
 
 def run_reference_arm(args):
+    """``--impl reference``: the CPU arm alone, ONE measured pass whatever --steps says (stated in ``steps_run``)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from gnngp_b200 import synth
     t0 = time.perf_counter()
-    samples = []
-    base = None
-    for i in range(max(1, min(args.steps, 2))):
-        args.seed = i
-        base = cpu_sampled_baseline(args)
-        samples.append(base["value"])
-    value = sum(samples) / len(samples)
-    base["value"] = value
+    try:
+        host = host_graph(args)
+        land = synth.draw_landmarks(host.train_mask, args.fraction, seed=args.seed)
+        base = cpu_arm(args, host, land)
+    except Exception as exc:
+        print(json.dumps({"impl": "reference", "unavailable": "CPU reference arm failed: %r" % (exc,)}), flush=True)
+        return
+    value = base["value"]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "device": "cpu", "wall_s": round(time.perf_counter() - t0, 1)},
+            "warmup": args.warmup, "steps_run": 1, "warmup_run": 0, "ms_per_step": value * 1e3, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "device": "cpu", "threads": base["cores"],
+                       "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "wall_s": round(time.perf_counter() - t0, 1),
+                       "note": "one bounded-sample pass of the unmodified reference functions on the same seeded graph as the "
+                               "GPU arm; an estimate of the full CPU run, see cpu_baseline.sample"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -230,12 +257,56 @@ def ncu_traffic(kernel: str, info: dict, k: int):
     SAME launch shape as the one timed here, else null."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            rec = json.load(fh)[kernel]
-        if int(rec["nnz"]) == int(info["nnz"]) and int(rec["n"]) == int(info["nodes"]) and int(rec["k"]) == int(k):
-            return float(rec["dram_bytes_per_launch"])
+            table = json.load(fh)
+        for rec in table.get(kernel, []) if isinstance(table.get(kernel), list) else [table[kernel]]:
+            if int(rec["nnz"]) == int(info["nnz"]) and int(rec["n"]) == int(info["nodes"]) and int(rec["k"]) == int(k):
+                return float(rec["dram_bytes_per_launch"])
     except Exception:
         pass
     return None
+
+
+def load_peaks() -> dict:
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks.update(json.load(fh)); peaks["source"] = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return peaks
+
+
+def spmm_roofline(spmm_calls, info, peaks, kernel_names) -> dict:
+    """Roofline of the sparse product with the most nnz x k (the layer-2 propagation): regime from
+    max(bytes / HBM peak, flops / fp32 FMA peak), SURVEY.md §8d."""
+    work = max(i[1] * i[2] for i, _ in spmm_calls)
+    big = [(i, ms) for i, ms in spmm_calls if i[1] * i[2] == work]
+    (rows, nnz, k), _ = big[0]
+    ms = sum(m for _, m in big) / len(big)
+    n_cols = info["nodes"]
+    alg_bytes = 8.0 * nnz + 4.0 * (rows + 1) + 4.0 * n_cols * k + 4.0 * rows * k
+    flops = 2.0 * nnz * k
+    fma_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12          # fp32 CUDA-core TFLOP/s at max clock
+    t_hbm = alg_bytes / (peaks["hbm_gbs"] * 1e9)
+    t_fma = flops / (fma_peak * 1e12)
+    hbm_view = {"achieved_gbs": round(alg_bytes / (ms * 1e-3) / 1e9, 2), "peak_gbs": peaks["hbm_gbs"],
+                "frac": round(alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 5)}
+    kernel = kernel_names.get(k, "spmm kernel")
+    common = {"kernel": "%s (layer-2 propagation A @ Ny, rows=%d nnz=%d k=%d)" % (kernel, rows, nnz, k), "ms_per_launch": round(ms, 3),
+              "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops, "t_roof_ms": round(max(t_hbm, t_fma) * 1e3, 3),
+              "t_hbm_ms": round(t_hbm * 1e3, 3), "t_fma_ms": round(t_fma * 1e3, 3), "peak_source": peaks["source"],
+              "traffic": ncu_traffic(kernel, info, k), "l2_gather_bytes": 4.0 * nnz * k,
+              "l2_gather_tbs": round(4.0 * nnz * k / (ms * 1e-3) / 1e12, 3), "hbm_view": hbm_view}
+    if t_hbm >= t_fma:
+        common.update({"bound": "hbm", "achieved": hbm_view["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": hbm_view["frac"]})
+    else:
+        tf = flops / (ms * 1e-3) / 1e12
+        common.update({"bound": "fp32-fma", "achieved": round(tf, 2), "peak": round(fma_peak, 1), "unit": "TFLOP/s",
+                       "frac": round(tf / fma_peak, 4),
+                       "note": "average degree %.0f puts this launch above the HBM/FMA crossover (SURVEY §8d): bound = fp32 FMA issue; "
+                               "the resource it actually saturates is the L2->SM gather path (l2_gather_tbs), 4 bytes per FMA" % (nnz / max(rows, 1))})
+    return common
 
 
 def run_ours(args):
@@ -244,6 +315,7 @@ def run_ours(args):
     from gnngp_b200.gnngp import GNNGP
     from gnngp_b200.ops import default_ops
     from gnngp_b200.profiling import OpTimer
+    import cases
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -261,18 +333,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic inputs, generated on the device (identical on every rank: same seed, same generator)
-    data = synth.make_graph(args.shape, seed=args.seed, device=dev, normalization="sym")
-    land = synth.draw_landmarks(data.train_mask, args.fraction, seed=args.seed)
+    t_setup = time.perf_counter()
+    data, host = device_graph(args, dev, world, rank)
+    land = synth.draw_landmarks(data.train_mask.cpu(), args.fraction, seed=args.seed).to(dev)      # host RNG: same set everywhere
     nugget = synth.nugget_grid(dev)
     info = synth.describe(data)
     info["landmarks"] = int(land.sum())
+    setup_s = time.perf_counter() - t_setup
 
-    if world == 1:
-        model = GNNGP(data, device=dev, Nystrom=True)
-    else:
+    def make_model():
+        if world == 1:
+            return GNNGP(data, device=dev, Nystrom=True)
         from gnngp_b200.shard import ShardedGNNGP
-        model = ShardedGNNGP(data, device=dev, Nystrom=True)
+        return ShardedGNNGP(data, device=dev, Nystrom=True)
+
+    model = make_model()
     model.mask["landmark"] = land
 
     def step():
@@ -310,32 +385,13 @@ def run_ours(args):
     table = timer.summary()
     spmm_calls = timer.calls("spmm") + timer.calls("spmm_panels")
     fit_solver = getattr(getattr(model, "pipe", None), "last_fit_solver", None) or "eigh"
+    best = {k: float(summary[k]) for k in ("train", "val", "test", "nugget")}
 
-    # ---- roofline of the dominant kernel: the layer-2 SpMM (largest k)
-    peaks = {"hbm_gbs": 6650.0, "source": "fallback"}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh); peaks["source"] = "measured"
-    except Exception:
-        pass
-    roof = None
-    if spmm_calls:
-        work = max(i[1] * i[2] for i, _ in spmm_calls)            # the launch with the most nnz x k: layer-2 A @ E
-        big = [(i, ms) for i, ms in spmm_calls if i[1] * i[2] == work]
-        (rows, nnz, k), _ = big[0]
-        ms = sum(m for _, m in big) / len(big)
-        n_cols = info["nodes"]
-        alg_bytes = 8.0 * nnz + 4.0 * (rows + 1) + 4.0 * n_cols * k + 4.0 * rows * k
-        achieved = alg_bytes / (ms * 1e-3) / 1e9
-        gather_bytes = 4.0 * nnz * k
-        roof = {"bound": "hbm", "kernel": "spmm_panel_kernel (layer-2 propagation A @ E, k=%d)" % k, "achieved": round(achieved, 2),
-                "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 5),
-                "traffic": ncu_traffic("spmm_panel_kernel", info, k), "ms_per_launch": round(ms, 3), "algorithmic_bytes": alg_bytes,
-                "l2_gather_bytes": gather_bytes, "l2_gather_tbs": round(gather_bytes / (ms * 1e-3) / 1e12, 3),
-                "fp32_tflops": round(2.0 * nnz * k / (ms * 1e-3) / 1e12, 2)}
+    peaks = load_peaks()
+    roof = spmm_roofline(spmm_calls, info, peaks, getattr(ops, "spmm_kernel_by_k", {})) if spmm_calls else None
 
-    # ---- tensor-core side: the largest tcgen05 launch of the step (the all-nugget posterior sweep at the default
-    # workload), plus the fused Gram + arc-cosine contraction; op times include the operand split pre-pass
+    # ---- tensor-core side: the largest tcgen05 launch of the step, plus the other two fused contractions; op times
+    # include the operand split pre-pass
     roof_tensor = None
     tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
 
@@ -356,11 +412,50 @@ def run_ours(args):
 
     entries = [e for e in (tensor_entry("nugget_sweep", "gemm_nt_tc3_kernel<EpiSweep>"),
                            tensor_entry("gemm_nt", "gemm_nt_tc3_kernel<EpiPlain>"),
+                           tensor_entry("syrk", "gemm_nt_tc3_kernel<EpiPlain, lower>"),
                            tensor_entry("gram_arccos", "gemm_nt_tc3_kernel<EpiArccos>")) if e is not None]
     if entries:
         entries.sort(key=lambda e: -e["flops"])
         roof_tensor = entries[0]
         roof_tensor["others"] = [{k: e[k] for k in ("kernel", "achieved", "frac", "ms_per_launch")} for e in entries[1:]]
+
+    # ---- samples of the timed run's outputs for the parity record (single GPU: Q and fit hold all rows)
+    n = info["nodes"]
+    sample_idx = torch.from_numpy(cases.sample_index(n, args.seed)).to(dev)
+    row_idx = torch.from_numpy(cases.big_row_sample(n, args.seed)).to(dev)
+    ours_headline = collect_samples(model, sample_idx, row_idx) if world == 1 else None
+
+    # ---- fraction-50 point of the landmark sweep (figure4.sh:2) + parity against the reference's golden fixture
+    sweep = None
+    parity_f50 = None
+    if not args.no_sweep and args.shape == "reddit" and args.fraction != 50:
+        land50 = synth.draw_landmarks(data.train_mask.cpu(), 50, seed=args.seed).to(dev)
+        model.mask["landmark"] = land50
+        for _ in range(2):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            s50 = step()
+        e1.record()
+        barrier()
+        t50 = torch.tensor([e0.elapsed_time(e1) / 1e3 / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t50, op=dist.ReduceOp.MAX)
+        sweep = [{"fraction": 50, "landmarks": int(land50.sum()), "value": round(float(t50), 5), "unit": UNIT, "steps": reps, "warmup": 2,
+                  "best": {k: float(s50[k]) for k in ("train", "val", "test", "nugget")}}]
+        golden = load_big_golden(GOLDEN_F50)
+        if world == 1 and golden is not None and args.seed == 0:
+            ours50 = collect_samples(model, sample_idx, row_idx, best=int(golden["best"]))
+            parity_f50 = parity_record(ours50, golden, "golden tests/golden/big/%s.npz (unmodified reference, CPU fp32 run)" % GOLDEN_F50)
+        model.mask["landmark"] = land
+    elif args.shape == "reddit" and args.fraction == 50 and world == 1 and args.seed == 0:
+        golden = load_big_golden(GOLDEN_F50)
+        if golden is not None:
+            ours50 = collect_samples(model, sample_idx, row_idx, best=int(golden["best"]))
+            parity_f50 = parity_record(ours50, golden, "golden tests/golden/big/%s.npz (unmodified reference, CPU fp32 run)" % GOLDEN_F50)
 
     # ---- end to end from pinned host buffers through the public API (N = 1 path; sharded: each rank its copy)
     e2e = None
@@ -374,25 +469,22 @@ def run_ours(args):
             mine = (src["edge_index"][0] >= lay.begin) & (src["edge_index"][0] < lay.end)
             src["edge_index"] = src["edge_index"][:, mine].contiguous()
             src["edge_attr"] = src["edge_attr"][mine].contiguous()
-        host = {k: v.cpu().pin_memory() for k, v in src.items()}
+        host_bufs = {k: v.cpu().pin_memory() for k, v in src.items()}
         del src
-        host["landmark"] = land.cpu().pin_memory()
+        host_bufs["landmark"] = land.cpu().pin_memory()
         host_nugget = nugget.cpu().pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in host.values()) + host_nugget.numel() * 4
+        h2d = sum(t.numel() * t.element_size() for t in host_bufs.values()) + host_nugget.numel() * 4
         from gnngp_b200.datasets import GraphData
-
-        stream_upload = STREAM_UPLOAD_AUTO.get(world, "0") if args.stream_upload == "auto" else args.stream_upload
-        os.environ["GNNGP_STREAM_UPLOAD"] = stream_upload
+        os.environ["GNNGP_STREAM_UPLOAD"] = args.stream_upload
 
         def e2e_step():
             ops.clear_cache()
-            # the small inputs first: host->device copies execute in issue order, so a copy issued after the edge
-            # list would wait for all of it (and hold back the stream that waits for that copy)
-            land_dev = host["landmark"].to(dev, non_blocking=True)
+            # the small inputs first: host->device copies execute in issue order
+            land_dev = host_bufs["landmark"].to(dev, non_blocking=True)
             nugget_dev = host_nugget.to(dev, non_blocking=True)
             # the call a user of the reference makes: host data + a device; the model moves it (src/gnngp.py:69)
-            g = GraphData(host["x"], host["y"], host["edge_index"], host["edge_attr"], host["train_mask"], host["val_mask"],
-                          host["test_mask"])
+            g = GraphData(host_bufs["x"], host_bufs["y"], host_bufs["edge_index"], host_bufs["edge_attr"], host_bufs["train_mask"],
+                          host_bufs["val_mask"], host_bufs["test_mask"])
             if world == 1:
                 m = GNNGP(g, device=dev, Nystrom=True)
             else:
@@ -423,29 +515,61 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(moved)                       # whole-job bytes: sum over ranks
         e2e = {"value": round(float(e2e_s), 4), "unit": UNIT, "h2d_bytes_per_step": int(moved[0]), "d2h_bytes_per_step": int(moved[1]),
-               "stream_upload": stream_upload == "1",
+               "steps_run": reps, "stream_upload": args.stream_upload == "1",
                # the end-to-end run must reproduce the metrics of the HBM-resident run (same inputs, same landmarks)
-               "matches_resident_run": bool(all(abs(a - float(summary[k])) <= 2e-3
-                                                for a, k in zip(e2e_out[:3], ("train", "val", "test"))))}
+               "matches_resident_run": bool(all(abs(a - best[k]) <= 2e-3 for a, k in zip(e2e_out[:3], ("train", "val", "test"))))}
+        del host_bufs
+    else:
+        del model
+    ops.clear_cache()
+    ops.release_workspace()
+    torch.cuda.empty_cache()
+
+    # ---- the unmodified reference on this GPU, same inputs (single GPU only) + live parity of the timed run
+    gpu_ref = None
+    parity_live = None
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            from baseline import ref_arm
+            gpu_ref, ref_samples = ref_arm.gpu_reference_full(data, land, nugget, args.layers, args.sigma_b, args.sigma_w,
+                                                              sample_idx, row_idx, steps=1)
+            if ref_samples is not None:
+                # compare at the REFERENCE's selected nugget
+                if ours_headline["best"] != ref_samples["best"]:
+                    gpu_ref["best_nugget_index_differs"] = [ours_headline["best"], ref_samples["best"]]
+                else:
+                    ref_samples["fit_scale"] = float(np.abs(ref_samples["fit_best"]).max())
+                    parity_live = parity_record(ours_headline, ref_samples, "live: unmodified reference (baseline/_ref) on this GPU, "
+                                                                            "same inputs, fraction %d" % args.fraction)
+                gpu_ref["speedup_value"] = round(gpu_ref["value"] / seconds, 2)
+        except Exception as exc:
+            gpu_ref = {"unavailable": "gpu reference failed: %r" % (exc,)}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                csr = ops.csr_of(torch.sparse_coo_tensor(data.edge_index, data.edge_attr, (info["nodes"],) * 2))
-                cpu = cpu_sampled_baseline(args, device_graph_for_cpu(data, csr), land.cpu().numpy())
+                cpu = cpu_arm(args, host, land.cpu())
             except Exception as exc:  # the CPU leg must never take the GPU number down with it
-                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (exc,)}
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (exc,)}
+        parity = {}
+        if parity_live is not None:
+            parity["fraction_%d" % args.fraction] = parity_live
+        if parity_f50 is not None:
+            parity["fraction_50"] = parity_f50
+        headline_parity = parity_live or parity_f50
+        config = {"workload": workload_name(args), "graph": info,
+                  "l2": "inputs larger than L2 (adjacency %.2f GB, factor %.2f GB)" % (info["nnz"] * 8 / 1e9, info["nodes"] * (info["landmarks"] + 1) * 4 / 1e9),
+                  "parallelism": "row-sharded x%d" % world if world > 1 else "single GPU",
+                  "fit_solver": fit_solver, "best": best, "setup_s": round(setup_s, 1),
+                  "parity_vs_reference": ({k: headline_parity[k] for k in ("qqT_rel", "fit_rel", "argmax_flips", "ok", "source")}
+                                          | {"cases": parity}) if headline_parity else None}
         line = {"metric": METRIC, "value": round(seconds, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(seconds * 1e3, 3), "higher_is_better": False,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args), "graph": info, "l2": "inputs larger than L2 (adjacency %.2f GB, factor %.2f GB)" % (
-                    info["nnz"] * 8 / 1e9, info["nodes"] * (info["landmarks"] + 1) * 4 / 1e9),
-                    "parallelism": "row-sharded x%d" % world if world > 1 else "single GPU",
-                    "fit_solver": fit_solver,
-                    "best": {k: float(summary[k]) for k in ("train", "val", "test", "nugget")}},
-                "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches), "roofline": roof, "roofline_tensor": roof_tensor,
-                "cpu_baseline": cpu,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
+                "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "sweep": sweep,
                 "stages_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}}
         if args.breakdown:
             with open(args.breakdown, "w") as fh:

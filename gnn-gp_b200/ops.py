@@ -64,6 +64,7 @@ class CudaOps(object):
         self._csr_cache = {}
         self.spmm_tile_cols = 0       # 0 = panel layout (default); 32/64/128 = row-major gather with that tile
         self.spmm_nnz_per_warp = 0
+        self.spmm_kernel_by_k = {}    # operand width -> name of the kernel the last product of that width ran (bench roofline)
 
     # ------------------------------------------------------------------ plumbing
     @staticmethod
@@ -168,21 +169,30 @@ class CudaOps(object):
         if not A.is_sparse:
             raise RuntimeError("gnngp_b200: adjacency must be a torch sparse COO tensor")
         idx, val = A._indices(), A._values()
-        key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index)
+        key = self._csr_key(A)
         hit = self._csr_cache.get(key)
         if hit is None:
             csr = self.csr_from_coo(idx[0], idx[1], val if val.dtype == torch.float32 else val.to(torch.float32),
                                     A.shape[0], A.shape[1])
             if len(self._csr_cache) >= 2:
                 self._csr_cache.clear()
-            # the entry keeps the COO tensors alive, so their addresses cannot be recycled for other data
-            # while the key is in the cache (in-place edits of A's values are not tracked)
+            # the entry keeps the COO tensors alive, so their addresses cannot be recycled for other data while
+            # the key is in the cache; in-place edits bump the tensors' version counters, which are part of the key
             hit = (csr, idx, val)
             self._csr_cache[key] = hit
         return hit[0]
 
+    @staticmethod
+    def _csr_key(A: torch.Tensor):
+        idx, val = A._indices(), A._values()
+        return (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index, idx._version, val._version)
+
     def clear_cache(self) -> None:
         self._csr_cache.clear()
+
+    def evict(self, A: torch.Tensor) -> None:
+        """Drop the cached CSR of this adjacency only."""
+        self._csr_cache.pop(self._csr_key(A), None)
 
     def register_streamed(self, A: torch.Tensor, plan: dict) -> ChunkedCsr:
         """Row-chunked CSR of an adjacency whose edge list is being uploaded in row-aligned pieces
@@ -222,7 +232,7 @@ class CudaOps(object):
                 blocks.append(block)
             in_range.record_stream(main)
         chunked = ChunkedCsr(n, int(A.shape[1]), blocks, in_range)
-        key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(A.shape), idx.device.index)
+        key = self._csr_key(A)
         if len(self._csr_cache) >= 2:
             self._csr_cache.clear()
         self._csr_cache[key] = (chunked, idx, val)
@@ -305,6 +315,7 @@ class CudaOps(object):
             padded = self.empty(B.shape[0], k, B.device)
             padded.copy_(B)
             B, ldb = padded, self._ld(padded)
+        self.spmm_kernel_by_k[int(k)] = "spmm_panel_kernel" if use_panels else "spmm_csr_kernel"
         self.lib.call("gnngp_spmm_csr_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(),
                       csr.n_rows, csr.n_cols, csr.nnz, B.data_ptr(), ldb, k, float(alpha), out.data_ptr(),
                       self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), wptr, need, self._stream())
@@ -323,6 +334,7 @@ class CudaOps(object):
         self._check(out, "out", dims=2)
         if out.shape != (csr.n_rows, k) or (k > 1 and out.stride(1) != 1):
             raise RuntimeError("spmm_panels: out must be a [%d x %d] row-major view" % (csr.n_rows, k))
+        self.spmm_kernel_by_k[int(k)] = "spmm_panel_kernel"
         self.lib.call("gnngp_spmm_panels_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(), csr.n_rows,
                       csr.n_cols, csr.nnz, panels_ptr, k, float(alpha), out.data_ptr(), self._ld(out),
                       int(self.spmm_nnz_per_warp), self._stream())
@@ -602,6 +614,45 @@ class CudaOps(object):
         self.lib.call("gnngp_sqerr_sum", fitted.data_ptr(), y.data_ptr(), membership.data_ptr(), G, n, k, sse.data_ptr(),
                       self._stream())
         return sse
+
+
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.device):
+            if a.type == "cuda":
+                return a
+        elif isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, CsrMatrix):
+            return a.colidx.device if a.colidx.is_cuda else None
+        elif isinstance(a, ChunkedCsr):
+            return a.in_range.device
+    return None
+
+
+def _guarded(fn):
+    """Run an operator with the CUDA device of its first tensor argument current.  The C ABI launches on the
+    runtime's current device and `_stream()` returns that device's current stream, so a model built with
+    ``device=cuda:1`` while device 0 is current would otherwise launch on GPU 0 against GPU-1 pointers (the
+    reference honours ``--device`` because torch ops guard themselves, src/main.py:68)."""
+    import functools
+
+    @functools.wraps(fn)
+    def run(self, *args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return run
+
+
+for _name, _fn in list(vars(CudaOps).items()):
+    if callable(_fn) and not _name.startswith("_") and not isinstance(_fn, (staticmethod, classmethod)) and _name not in (
+            "workspace", "release_workspace", "side_stream", "launch_count", "set_gemm_engine", "clear_cache"):
+        setattr(CudaOps, _name, _guarded(_fn))
+del _name, _fn
 
 
 _OPS = None

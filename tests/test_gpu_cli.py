@@ -37,3 +37,30 @@ def test_gnn_action_is_rejected(capsys):
     from gnngp_b200 import main as cli
     with pytest.raises(Exception, match="outside this package's scope"):
         cli.main(["cora", "gcn", "gnn"])
+
+
+@pytest.mark.parametrize("argv, shape, fraction", [(["cora", "gcn", "gp"], "cora", 0),
+                                                   (["pub", "gcn", "gp", "--fraction=4", "--runs", "1"], "pubmed", 4)])
+def test_cli_metrics_match_the_oracle_on_the_same_graph(capsys, argv, shape, fraction):
+    """the train / val / test figures the CLI prints at the selected nugget equal what the CPU
+    oracle (restatement of compute.py / predict.py, pinned to the reference's goldens) gets on the SAME synthetic
+    graph and the SAME landmark draw (the CLI's own: ``torch.manual_seed(123)`` then ``rand(N) < 1/fraction``,
+    src/main.py:95,111)."""
+    import numpy as np
+    import torch
+    from gnngp_b200 import synth
+    from gnngp_b200.datasets import transition_matrix
+    from oracle import gnngp_oracle as orc
+    table, _ = run_cli(argv, capsys)
+    dev = torch.device("cuda:0")
+    data = transition_matrix(normalization="sym")(synth.make_graph(shape, seed=0, device=dev, normalization=None))
+    masks = {"train": data.train_mask.cpu().numpy(), "val": data.val_mask.cpu().numpy(), "test": data.test_mask.cpu().numpy()}
+    if fraction:
+        torch.manual_seed(123)
+        masks["landmark"] = (data.train_mask & (torch.rand(data.num_nodes, device=dev) < 1 / fraction)).cpu().numpy()
+    ref = orc.run(data.x.cpu().numpy(), data.y.cpu().numpy(), data.edge_index[0].cpu().numpy(), data.edge_index[1].cpu().numpy(),
+                  data.edge_attr.cpu().numpy(), masks, torch.logspace(-3, 1, 101).numpy(), layers=2, sigma_b=0.0, sigma_w=1.0,
+                  nystrom=bool(fraction), method="GCN")
+    for col, key in ((1, "train"), (2, "val"), (3, "test")):
+        size = int(masks[key].sum())
+        assert abs(float(table[0, col]) - float(ref["summary"][key])) <= 2.5 / size + 1e-6, (key, float(table[0, col]), ref["summary"][key])
