@@ -41,16 +41,29 @@ class _TimedEigh(object):
     """Context manager that times every ``torch.linalg.eigh`` call made inside it (instrumentation only: the
     reference's code is not touched; the wrapper forwards to the real function)."""
 
+    def __init__(self, charge_instead: float = None):
+        # charge_instead: seconds to charge for an eigendecomposition that was ALREADY timed at the same size in
+        # this pass (the fit's m x m block after the landmark block's N_a x N_a, m = N_a + 1): the call is then
+        # answered with a placeholder decomposition (identity vectors) instead of being run a second time, to keep
+        # the bounded sample bounded (a CPU eigh of 15 404 rows costs about a minute).  Stated in the record.
+        self.charge_instead = charge_instead
+
     def __enter__(self):
         self.seconds = 0.0
         self.sizes = []
+        self.substituted = 0
         self._real = torch.linalg.eigh
 
         def timed(*args, **kwargs):
+            n = int(args[0].shape[-1])
+            self.sizes.append(n)
+            if self.charge_instead is not None:
+                self.seconds += self.charge_instead
+                self.substituted += 1
+                return torch.ones(n, dtype=args[0].dtype), torch.eye(n, dtype=args[0].dtype)
             t0 = time.perf_counter()
             out = self._real(*args, **kwargs)
             self.seconds += time.perf_counter() - t0
-            self.sizes.append(int(args[0].shape[-1]))
             return out
 
         torch.linalg.eigh = timed
@@ -144,10 +157,11 @@ def cpu_reference_sampled(data, land: torch.Tensor, nugget: torch.Tensor, layers
     del exxt_s
     y_t = y[t_rows]
     train_t = data.train_mask[t_rows]
-    with _TimedEigh() as eig2:
+    reuse = eig1.seconds * (m / float(na)) ** 3 if na >= 6000 else None
+    with _TimedEigh(charge_instead=reuse) as eig2:
         t0 = time.perf_counter()
         fit_t = ref_predict.fit_Nystrom(q_t, y_t, train_t, nugget)
-        stages["fit_sample_s"] = time.perf_counter() - t0
+        stages["fit_sample_s"] = time.perf_counter() - t0 + (eig2.seconds if reuse is not None else 0.0)
     stages["eigh_fit_s"] = eig2.seconds
     masks_t = {"train": train_t, "val": data.val_mask[t_rows], "test": data.test_mask[t_rows], "landmark": land[t_rows]}
     t0 = time.perf_counter()
@@ -171,9 +185,11 @@ def cpu_reference_sampled(data, land: torch.Tensor, nugget: torch.Tensor, layers
         "sample": ("unmodified reference functions (baseline/_ref compute.py / predict.py, torch %s CPU, fp32) on row samples "
                    "of the GPU arm's graph at full operand widths: sparse products on %d of %d rows (%d of %d nonzeros); "
                    "kernel layer on all %d landmark rows + %d others; fit and metrics on %d rows; both eigendecompositions "
-                   "(n = %d, %d) at full size, unscaled; row-proportional stage times scaled by the inverse sampling rate; "
+                   "(n = %d, %d) at full size, unscaled%s; row-proportional stage times scaled by the inverse sampling rate; "
                    "%.1f s of CPU work measured on %d threads" % (
-                       torch.__version__, sp_rows_n, n, nnz_sp, nnz_total, na, r, t_rows.numel(), na, m, measured, threads)),
+                       torch.__version__, sp_rows_n, n, nnz_sp, nnz_total, na, r, t_rows.numel(), na, m,
+                       " (the second one charged at the first one's measured time x (m/N_a)^3, not run again)" if reuse is not None else "",
+                       measured, threads)),
         "estimated_stages_s": {k: round(v, 3) for k, v in est.items()},
         "measured_stages_s": {k: round(v, 3) for k, v in stages.items()},
         "wall_s": round(time.perf_counter() - t_start, 1),

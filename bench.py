@@ -183,22 +183,43 @@ def collect_samples(model, sample_idx, row_idx, best=None) -> dict:
 
 def parity_record(ours: dict, ref: dict, source: str) -> dict:
     """qqT_rel / fit_rel / argmax_flips of ``ours`` against reference samples (same sample indices, same nugget).
-    A flip counts as "clear" when the reference's own top-2 margin at that node exceeds 1e-3 of its largest
-    posterior mean (near-ties flip between any two fp32 evaluations, the reference's fp64 run included)."""
+
+    Posterior means: the reference's own fp32 run differs from its fp64 run by 7e-3 (nugget 0.1) to 6e-2 (nugget
+    1e-3) on the Reddit shape (tests/golden/big, ``fit_*64``) — two fp32 evaluations are two draws of rounding noise
+    times the conditioning of ``Q_b^T Q_b + eps d I`` — so ``fit_rel`` is taken against the fp64 run when the source
+    has one and bounded by max(1e-4, 6 x that self-error); against an fp32-only source it is reported, not bounded.
+    A flip counts as "clear" when the reference's own top-2 margin at that node exceeds its fp32 noise (fp64 companion)
+    or 1e-3 of its largest posterior mean."""
     flips = ours["pred_best"].astype(np.int64) != np.asarray(ref["pred_best"]).astype(np.int64)
-    rec = {"source": source, "nugget_index": int(ref["best"]),
-           "qqT_rel": rel_fro(ours["ksamp"], ref["ksamp"]),
-           "fit_rel": rel_fro(ours["fit_best"], ref["fit_best"]), "fit_rel_nugget_0.1": rel_fro(ours["fit_mid"], ref["fit_mid"]),
+    rec = {"source": source, "nugget_index": int(ref["best"]), "qqT_rel": rel_fro(ours["ksamp"], ref["ksamp"]),
            "argmax_flips": int(flips.sum()), "argmax_nodes": int(flips.size)}
+    fit_ok = True
+    if "fit_best64" in ref:
+        rec["qqT_rel_fp64"] = rel_fro(ours["ksamp"], ref["ksamp64"])
+        for key, tag in (("fit_best", "fit_rel"), ("fit_mid", "fit_rel_nugget_0.1")):
+            floor = rel_fro(ref[key], ref[key + "64"])
+            rec[tag] = rel_fro(ours[key], ref[key + "64"])
+            rec[tag + "_reference_fp32_self_error"] = float("%.3e" % floor)
+            rec[tag + "_vs_fp32_run"] = float("%.3e" % rel_fro(ours[key], ref[key]))
+            fit_ok = fit_ok and rec[tag] <= max(1e-4, 6.0 * floor)
+        rec["fit_rel_against"] = "the reference's fp64 run"
+        noise = float(np.max(np.abs(ref["fit_best"].astype(np.float64) - ref["fit_best64"])))
+    else:
+        rec["fit_rel"] = rel_fro(ours["fit_best"], ref["fit_best"])
+        rec["fit_rel_nugget_0.1"] = rel_fro(ours["fit_mid"], ref["fit_mid"])
+        rec["fit_rel_against"] = "the reference's fp32 run (no fp64 companion: reported, not bounded)"
+        noise = None
     if "margin_best" in ref:
         scale = float(ref.get("fit_scale", np.abs(ref["fit_best"]).max()))
-        rec["argmax_flips_clear_margin"] = int((flips & (np.asarray(ref["margin_best"]) > 1e-3 * scale)).sum())
+        tol = (2.0 * noise + 1e-5 * scale) if noise is not None else 1e-3 * scale
+        rec["argmax_flips_clear_margin"] = int((flips & (np.asarray(ref["margin_best"]) > tol)).sum())
     curves = ref.get("curves") or {k: ref["result_" + k] for k in ("train", "val", "test")}
     rec["curve_max_abs_diff"] = float(max(np.abs(ours["curves"][k] - np.asarray(curves[k])).max() for k in ("train", "val", "test")))
-    rec["ok"] = bool(rec["qqT_rel"] <= 1e-4 and rec["fit_rel_nugget_0.1"] <= 1e-3 and rec.get("argmax_flips_clear_margin", 0) == 0
+    rec["ok"] = bool(rec["qqT_rel"] <= 1e-4 and fit_ok and rec.get("argmax_flips_clear_margin", 0) == 0
                      and rec["curve_max_abs_diff"] <= 2e-3)
-    for k in ("qqT_rel", "fit_rel", "fit_rel_nugget_0.1", "curve_max_abs_diff"):
-        rec[k] = float("%.3e" % rec[k])
+    for k in ("qqT_rel", "qqT_rel_fp64", "fit_rel", "fit_rel_nugget_0.1", "curve_max_abs_diff"):
+        if k in rec:
+            rec[k] = float("%.3e" % rec[k])
     return rec
 
 

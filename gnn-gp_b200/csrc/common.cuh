@@ -45,6 +45,10 @@ inline bool aligned(const void *p, size_t bytes) { return (reinterpret_cast<uint
 
 int sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: set it once per
+// (kernel, device) — a second GPU used from the same process needs its own call.
+cudaError_t ensure_dynamic_smem(const void *kernel, int bytes);
+
 // ReLU arc-cosine expectation J1 applied to a normalised correlation, rescaled by the two norms.
 // Mirrors src/compute.py:115-116 / 125-126: c = clamp((g / s) / t, -1, 1) (NaN propagates, like
 // torch.clamp), theta = acos c, E = (1/2pi) (sin theta + (pi - theta) cos theta) * s * t.

@@ -17,36 +17,53 @@ static bool use_tensor_cores(int64_t M, int64_t N, int64_t K)
 {
     const int engine = g_gemm_engine.load();
     if (engine == 0 || K <= 0) return false;
-    if (engine == 1 || engine == 3 || engine == 4) return true;
-    // auto: enough 128x256 tiles to occupy a good part of the chip and a K loop worth pipelining
-    return ceil_div(M, tc::v2::BM) * ceil_div(N, tc::v2::BN) >= 64 && K >= 128;
+    if (engine == 1) return true;
+    // auto: enough output to occupy a good part of the chip and a K loop worth pipelining
+    return ceil_div(M, 128) * ceil_div(N, 128) >= 64 && K >= 128;
 }
 
 template <class Epi>
 static int contract(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                     const Epi &epi, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    // engine 3 = the unchunked 128x256 tcgen05 kernel (faster, but its long TMEM accumulation is biased:
-    // kept for measurement only); engines 1 / 2 use the chunked-accumulation kernel
-    // engine 4 = chunked 128x128 kernel (v2); engines 1 / 2 = chunked 128x256 kernel with two epilogue warpgroups (v3)
-    if (use_tensor_cores(M, N, K)) {
-        const int engine = g_gemm_engine.load();
-        return tc::gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, ws, ws_bytes, st, engine != 3, false, engine != 4);
-    }
+    if (use_tensor_cores(M, N, K))
+        return tc::gemm_nt_tc<Epi, Epi>(A, lda, B, ldb, M, N, K, epi, nullptr, ws, ws_bytes, st, false);
     return gemm_nt_simt(A, lda, B, ldb, M, N, K, epi, st);
 }
 
 __global__ void laplacian_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, const float *__restrict__ R,
                                  int64_t ldr, int64_t r, int64_t f, float gamma, float *__restrict__ C0, int64_t ldc)
 {
-    // one warp per output element block: thread (i, j) loops over features; small shapes only
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i = blockIdx.y;
-    if (j >= r || i >= n) return;
-    const float *x = X + i * ldx, *y = R + j * ldr;
-    float acc = 0.0f;
-    for (int64_t q = 0; q < f; ++q) acc += fabsf(__ldg(x + q) - __ldg(y + q));
-    C0[i * ldc + j] = expf(-gamma * acc);
+    // L1 distances have no contraction form: a 32 x 32 output tile per block, the two 32-row feature slabs staged
+    // through shared memory 32 features at a time (coalesced loads, conflict-free reads); any n, r (grid-stride tiles)
+    __shared__ float xs[32][33], ys[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8 threads, 4 output rows per thread
+    const int64_t tiles_c = ceil_div(r, 32), tiles = ceil_div(n, 32) * tiles_c;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t i0 = (tile / tiles_c) * 32, j0 = (tile % tiles_c) * 32;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int64_t q0 = 0; q0 < f; q0 += 32) {
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int rr = ty + 8 * e;
+                xs[rr][tx] = (i0 + rr < n && q0 + tx < f) ? __ldg(X + (i0 + rr) * ldx + q0 + tx) : 0.0f;
+                ys[rr][tx] = (j0 + rr < r && q0 + tx < f) ? __ldg(R + (j0 + rr) * ldr + q0 + tx) : 0.0f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) {
+                const float yv = ys[tx][q];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] += fabsf(xs[ty + 8 * e][q] - yv);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i0 + ty + 8 * e, j = j0 + tx;
+            if (i < n && j < r) C0[i * ldc + j] = expf(-gamma * acc[e]);
+        }
+    }
 }
 
 __global__ void reciprocal_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ out)
@@ -96,10 +113,14 @@ int gnngp_syrk_f32(const float *A, int64_t lda, float *C, int64_t ldc, int64_t n
     if (n == 0) return GNNGP_OK;
     cudaStream_t st = as_stream(stream);
     EpiPlain epi{C, ldc, 1.0f, 0.0f, aligned(C, 16) && ldc % 4 == 0};
-    if (use_tensor_cores(n, n, K) && g_gemm_engine.load() != 3) {
-        // the operand is split once and used on both sides; tiles above the diagonal are skipped (their
-        // entries keep whatever C held: callers zero C, the eigensolver only reads the lower triangle)
-        return tc::gemm_nt_tc(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st, true, true, false);
+    if (use_tensor_cores(n, n, K)) {
+        // the operand is split once and used on both sides; tiles wholly above the diagonal are skipped (their
+        // entries keep whatever C held: the eigensolver only reads the lower triangle).  A tile grid that does not
+        // fill the chip a few times (156 tiles at Reddit fraction 50, K = 153 k) splits K over several work units
+        // that accumulate atomically, so C is zeroed here first.
+        GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)n * sizeof(float), (size_t)n, st));
+        EpiAtomicAdd split{C, ldc, 1.0f};
+        return tc::gemm_nt_tc<EpiPlain, EpiAtomicAdd>(A, lda, A, lda, n, n, K, epi, &split, workspace, workspace_bytes, st, true);
     }
     return contract(A, lda, A, lda, n, n, K, epi, workspace, workspace_bytes, st);
 }
@@ -145,9 +166,9 @@ int gnngp_laplacian_kernel_f32(const float *X, int64_t ldx, int64_t n, const flo
                                float gamma, float *C0, int64_t ldc, gnngp_stream_t stream)
 {
     GNNGP_REQUIRE(n >= 0 && r >= 0 && f > 0 && ldx >= f && ldr >= f && ldc >= r, "laplacian_kernel: bad sizes");
-    GNNGP_REQUIRE(n <= 65535, "laplacian_kernel: n = %lld exceeds the grid limit of this small-shape kernel", (long long)n);
     if (n == 0 || r == 0) return GNNGP_OK;
-    laplacian_kernel<<<dim3((unsigned)ceil_div(r, 128), (unsigned)n), 128, 0, as_stream(stream)>>>(X, ldx, n, R, ldr, r, f, gamma, C0, ldc);
+    const int64_t tiles = ceil_div(n, 32) * ceil_div(r, 32);
+    laplacian_kernel<<<(unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 16), 256, 0, as_stream(stream)>>>(X, ldx, n, R, ldr, r, f, gamma, C0, ldc);
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }

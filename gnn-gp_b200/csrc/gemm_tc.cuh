@@ -8,15 +8,24 @@
 // and each K-step issues three tensor-core MMAs  lo*hi + hi*lo + hi*hi  into one fp32 TMEM
 // accumulator (the dropped lo*lo term is ~2^-24).
 //
-// Kernel anatomy (one persistent CTA per SM, 256 threads):
-//   warp 0   TMA producer     cp.async.bulk.tensor (128B swizzle) -> 2-stage smem ring, 96 KB / stage
-//   warp 1   MMA issuer       one lane issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8
-//   warp 2   TMEM allocator   512 columns = two 128x256 fp32 accumulators (ping-pong)
-//   warp 4-7 epilogue         tcgen05.ld 32 lanes x 32 columns -> fused epilogue functor -> global
-// mbarriers: full/empty per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator
-// (MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Kernel anatomy (ONE kernel template; one persistent CTA per SM, 384 threads):
+//   warp 0    TMA producer     cp.async.bulk.tensor (128B swizzle) -> 2-stage smem ring, 96 KB / stage
+//   warp 1    MMA issuer       one lane issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8
+//   warp 2    TMEM allocator   512 columns = two 128x256 fp32 partial sums (ping-pong)
+//   warp 4-11 epilogue         two warpgroups, one per 128-column half of the tile: tcgen05.ld 32 lanes x 32
+//                              columns, partial sums added into a REGISTER master accumulator (see below),
+//                              then the fused epilogue functor -> global
+// mbarriers: full/empty per smem stage (TMA <-> MMA), tmem_full/tmem_empty per partial-sum buffer
+// (MMA <-> epilogue).  `setmaxnreg` moves registers from the control warps (40) to the epilogue (232).
 // Tiles are rasterised in groups of 12 row-blocks x all column-blocks so the ~148 tiles in flight
-// share A and B panels through the L2.
+// share A and B panels through the L2; symmetric products enumerate only tiles that touch the lower
+// triangle; skinny outputs with a long contraction split K over several work units (atomic epilogue).
+//
+// Chunked accumulation.  Measured on B200: tcgen05.mma adds into the TMEM accumulator with truncation, so a
+// long K loop accumulates a bias of ~0.5 ulp(acc) per MMA (2e-5 relative at K = 3 070, 1.7e-3 for the train
+// Gram with K = N_t = 153 k) — far above the fp32 reference.  Every TMEM partial sum is therefore kept to
+// CHUNK_KB k-blocks (128 K-elements = 48 MMAs, starting from zero) and the epilogue threads add the partials
+// into their master row with round-to-nearest adds (rel. error 9e-7 ... 1.2e-6 against fp64 for K up to 153 k).
 #pragma once
 #include <cuda.h>
 
@@ -30,11 +39,15 @@ constexpr int UMMA_K = 8;                        // tf32: 32 bytes per MMA K-ste
 constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * BK * 4;
 constexpr int B_BYTES = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 96 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;                                           // 4 control warps + two epilogue warpgroups
 constexpr int TMEM_COLS = 512;
+constexpr int PARTIALS = 2;                                            // 2 x 256 TMEM columns
+constexpr int HALF = BN / 2;                                           // columns per epilogue warpgroup
+constexpr int CHUNK_KB = 4;                                            // k-blocks per partial sum (128 K-elements)
 constexpr int GROUP_M = 12;
+constexpr int MAX_SPLITS = 8;
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,351 +169,45 @@ __device__ __forceinline__ TileCoord raster(int64_t tile, int64_t tiles_m, int64
     return t;
 }
 
-template <class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, Epi epi)
+// Tiles of a symmetric product that touch the lower triangle.  A 128 x 256 tile (i, j) does when 256 j <= 128 i + 127,
+// i.e. j <= i / 2: row-blocks 2p and 2p+1 have p + 1 tiles each, p (p + 1) tiles precede the pair.
+__host__ __device__ inline int64_t lower_tile_count(int64_t tiles_m)
 {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t *smem = smem_raw + (base - raw);
-    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
-    // barrier slots (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
-    fence_before();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int64_t total = tiles_m * tiles_n;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord tc_ = raster(tile, tiles_m, tiles_n);
-                const int32_t m0 = (int32_t)(tc_.m_blk * BM), n0 = (int32_t)(tc_.n_blk * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t dst = base + stage * STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(dst + A_BYTES, &map_a_lo, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(dst + 2 * A_BYTES, &map_b_hi, full_bar(stage), kb * BK, n0);
-                    tma_load_2d(dst + 2 * A_BYTES + B_BYTES, &map_b_lo, full_bar(stage), kb * BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    fence_after();
-                    const uint32_t a_hi = base + stage * STAGE_BYTES;
-                    const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                    const uint32_t b_lo = b_hi + B_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t off = k * UMMA_K * 4;
-                        const uint64_t dah = smem_desc(a_hi + off), dal = smem_desc(a_lo + off);
-                        const uint64_t dbh = smem_desc(b_hi + off), dbl = smem_desc(b_lo + off);
-                        umma_tf32(tmem_d, dal, dbh, kInstrDesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_tf32(tmem_d, dah, dbl, kInstrDesc, 1u);
-                        umma_tf32(tmem_d, dah, dbh, kInstrDesc, 1u);
-                    }
-                    umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-                umma_commit(tfull_bar(acc));         // accumulator complete
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
-            }
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> fused functor -> global =====
-        const int wq = warp - 4;                       // TMEM lane quarter this warp may read
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const TileCoord tc_ = raster(tile, tiles_m, tiles_n);
-            mbar_wait(tfull_bar(acc), acc_phase);
-            fence_after();
-            const int64_t row = tc_.m_blk * BM + wq * 32 + lane;
-            const int64_t col0 = tc_.n_blk * BN;
-#pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
-                float v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + cc * 32);
-                tmem_ld32(taddr, v);
-                const int64_t c = col0 + cc * 32;
-                if (row < M && c < N) {
-                    if (epi.vec_ok && c + 32 <= N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) epi.vec4(row, c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c + j < N) epi(row, c + j, v[j]);
-                    }
-                }
-            }
-            fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
-        }
-    }
-    fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
+    const int64_t p = tiles_m / 2;
+    return p * (p + 1) + ((tiles_m & 1) ? p + 1 : 0);
 }
-
-// =============================================================================================
-// v2: chunked accumulation (the default tensor-core engine)
-//
-// Measured on B200: tcgen05.mma adds into the TMEM accumulator with truncation, so a long K loop
-// accumulates a bias of ~0.5 ulp(acc) per MMA (2e-5 relative at K = 3 070, 1.7e-3 for the train Gram
-// with K = N_t = 153 k) — far above the fp32 reference.  v2 keeps each TMEM partial sum short
-// (CHUNK_KB k-blocks = 128 K-elements = 48 MMAs, starting from zero) and lets the epilogue warps add the
-// partials into a 128-column fp32 master accumulator held in REGISTERS with round-to-nearest adds.
-// Tile 128 x 128 so that one thread's master row fits the register file; four 128-column TMEM partial
-// buffers (all 512 columns) keep the MMA issuer up to four chunks ahead of the epilogue, which hides
-// the fused epilogue (arc-cosine / scatter) of the previous tile.
-namespace v2 {
-
-constexpr int BM = 128, BN = 128;
-constexpr int STAGES = 3;
-constexpr int A_BYTES = BM * BK * 4;
-constexpr int B_BYTES = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 64 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int PARTIALS = 4;                                            // 4 x 128 TMEM columns
-constexpr int CHUNK_KB = 4;                                            // k-blocks per partial sum (128 K-elements)
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-// lower-triangular tile enumeration for symmetric products (A == B): t -> (i, j), j <= i, row by row
 __device__ __forceinline__ TileCoord raster_lower(int64_t t)
 {
-    int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= t) ++i;
-    while (i * (i + 1) / 2 > t) --i;
+    int64_t p = (int64_t)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((p + 1) * (p + 2) <= t) ++p;
+    while (p * (p + 1) > t) --p;
+    const int64_t r = t - p * (p + 1);
     TileCoord c;
-    c.m_blk = i;
-    c.n_blk = t - i * (i + 1) / 2;
+    if (r <= p) { c.m_blk = 2 * p; c.n_blk = r; }
+    else { c.m_blk = 2 * p + 1; c.n_blk = r - (p + 1); }
     return c;
+}
+
+// Work unit u = (tile, K split): tile = u / splits, this unit contracts k-blocks [kb0, kb1).
+struct Unit { TileCoord tile; int kb0, kb1; };
+template <bool LOWER>
+__device__ __forceinline__ Unit unit_of(int64_t u, int64_t tiles_m, int64_t tiles_n, int splits, int k_blocks)
+{
+    const int64_t t = u / splits;
+    const int sp = (int)(u - t * splits);
+    const int per = (k_blocks + splits - 1) / splits;
+    Unit w;
+    w.tile = LOWER ? raster_lower(t) : raster(t, tiles_m, tiles_n);
+    w.kb0 = min(k_blocks, sp * per);
+    w.kb1 = min(k_blocks, w.kb0 + per);
+    return w;
 }
 
 template <class Epi, bool LOWER>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_nt_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, Epi epi)
-{
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t *smem = smem_raw + (base - raw);
-    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + PARTIALS + a); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * PARTIALS));
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < PARTIALS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), TMEM_COLS);
-    fence_before();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int64_t total = LOWER ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
-    const int chunks = (k_blocks + CHUNK_KB - 1) / CHUNK_KB;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
-                const int32_t m0 = (int32_t)(tc_.m_blk * BM), n0 = (int32_t)(tc_.n_blk * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t dst = base + stage * STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(dst + A_BYTES, &map_a_lo, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(dst + 2 * A_BYTES, &map_b_hi, full_bar(stage), kb * BK, n0);
-                    tma_load_2d(dst + 2 * A_BYTES + B_BYTES, &map_b_lo, full_bar(stage), kb * BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer: one short partial sum per chunk, round-robin over the TMEM buffers =====
-            int stage = 0, part = 0;
-            uint32_t phase = 0, part_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                for (int ch = 0; ch < chunks; ++ch) {
-                    mbar_wait(tempty_bar(part), part_phase ^ 1u);
-                    fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(part * BN);
-                    const int kb_end = min(k_blocks, (ch + 1) * CHUNK_KB);
-                    for (int kb = ch * CHUNK_KB; kb < kb_end; ++kb) {
-                        mbar_wait(full_bar(stage), phase);
-                        fence_after();
-                        const uint32_t a_hi = base + stage * STAGE_BYTES;
-                        const uint32_t a_lo = a_hi + A_BYTES;
-                        const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                        const uint32_t b_lo = b_hi + B_BYTES;
-                        const bool first_kb = (kb == ch * CHUNK_KB);
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint32_t off = k * UMMA_K * 4;
-                            const uint64_t dah = smem_desc(a_hi + off), dal = smem_desc(a_lo + off);
-                            const uint64_t dbh = smem_desc(b_hi + off), dbl = smem_desc(b_lo + off);
-                            // small terms first, so they are not absorbed by a large running sum
-                            umma_tf32(tmem_d, dal, dbh, kInstrDesc, (first_kb && k == 0) ? 0u : 1u);
-                            umma_tf32(tmem_d, dah, dbl, kInstrDesc, 1u);
-                            umma_tf32(tmem_d, dah, dbh, kInstrDesc, 1u);
-                        }
-                        umma_commit(empty_bar(stage));
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                    umma_commit(tfull_bar(part));
-                    if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue warps: master accumulator in registers, RN adds of the TMEM partial sums =====
-        const int wq = warp - 4;
-        int part = 0;
-        uint32_t part_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
-            float master[BN];
-#pragma unroll
-            for (int j = 0; j < BN; ++j) master[j] = 0.0f;
-            for (int ch = 0; ch < chunks; ++ch) {
-                mbar_wait(tfull_bar(part), part_phase);
-                fence_after();
-#pragma unroll
-                for (int cc = 0; cc < BN / 32; ++cc) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(part * BN + cc * 32), v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) master[cc * 32 + j] += v[j];
-                }
-                fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(part));
-                if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
-            }
-            const int64_t row = tc_.m_blk * BM + wq * 32 + lane;
-            const int64_t col0 = tc_.n_blk * BN;
-            if (row < M) {
-                if (epi.vec_ok && col0 + BN <= N) {
-#pragma unroll
-                    for (int j = 0; j < BN; j += 4) epi.vec4(row, col0 + j, master[j], master[j + 1], master[j + 2], master[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < BN; ++j)
-                        if (col0 + j < N) epi(row, col0 + j, master[j]);
-                }
-            }
-        }
-    }
-    fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-}  // namespace v2
-
-// =============================================================================================
-// v3: chunked accumulation on the 128 x 256 tile (default)
-//
-// v2's 128 x 128 tile needs 85 B/cycle/SM of operand traffic at full tensor rate and is L2-bound
-// (57-74 % tensor-pipe active, profiles/r1/call4_ncu_full_summary.txt).  v3 keeps the register master
-// accumulator but restores the 128 x 256 tile (64 B/cycle/SM, the shape that reached 77-79 % unchunked):
-// 384 threads = 4 control warps + TWO epilogue warpgroups, each thread holding the 128 master columns of
-// its row for one half of the tile; `setmaxnreg` moves registers from the control warps (40) to the
-// epilogue warpgroups (232).  TMEM holds two 256-column partial sums (ping-pong), smem two 96 KB stages.
-namespace v3 {
-
-constexpr int BM = 128, BN = 256;
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 4;
-constexpr int B_BYTES = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                 // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int PARTIALS = 2;                                            // 2 x 256 TMEM columns
-constexpr int THREADS3 = 384;                                          // 4 control warps + two epilogue warpgroups
-constexpr int HALF = BN / 2;                                           // columns per epilogue warpgroup
-constexpr int CHUNK_KB = 4;                                            // k-blocks per partial sum (128 K-elements)
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-// lower-triangular tile enumeration for symmetric products (A == B): t -> (i, j), j <= i, row by row
-__device__ __forceinline__ TileCoord raster_lower(int64_t t)
-{
-    int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= t) ++i;
-    while (i * (i + 1) / 2 > t) --i;
-    TileCoord c;
-    c.m_blk = i;
-    c.n_blk = t - i * (i + 1) / 2;
-    return c;
-}
-
-template <class Epi, bool LOWER>
-__global__ void __launch_bounds__(THREADS3, 1)
 gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, Epi epi)
+                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, int splits, Epi epi)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -527,8 +234,7 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t total = LOWER ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
-    const int chunks = (k_blocks + CHUNK_KB - 1) / CHUNK_KB;
+    const int64_t total = (LOWER ? lower_tile_count(tiles_m) : tiles_m * tiles_n) * splits;
 
     // Register re-balancing is warpgroup-wide and scoped like in the CUTLASS warp-specialised kernels: the
     // control warpgroup shrinks to 40 registers at the top of ITS branch, the epilogue warpgroups grow to 232
@@ -540,10 +246,10 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
-                const int32_t m0 = (int32_t)(tc_.m_blk * BM), n0 = (int32_t)(tc_.n_blk * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+            for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
+                const Unit w = unit_of<LOWER>(u, tiles_m, tiles_n, splits, k_blocks);
+                const int32_t m0 = (int32_t)(w.tile.m_blk * BM), n0 = (int32_t)(w.tile.n_blk * BN);
+                for (int kb = w.kb0; kb < w.kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t dst = base + stage * STAGE_BYTES;
                     mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -560,20 +266,21 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             // ===== MMA issuer: one short partial sum per chunk, round-robin over the TMEM buffers =====
             int stage = 0, part = 0;
             uint32_t phase = 0, part_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                for (int ch = 0; ch < chunks; ++ch) {
+            for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
+                const Unit w = unit_of<LOWER>(u, tiles_m, tiles_n, splits, k_blocks);
+                for (int c0 = w.kb0; c0 < w.kb1; c0 += CHUNK_KB) {
                     mbar_wait(tempty_bar(part), part_phase ^ 1u);
                     fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(part * BN);
-                    const int kb_end = min(k_blocks, (ch + 1) * CHUNK_KB);
-                    for (int kb = ch * CHUNK_KB; kb < kb_end; ++kb) {
+                    const int kb_end = min(w.kb1, c0 + CHUNK_KB);
+                    for (int kb = c0; kb < kb_end; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         fence_after();
                         const uint32_t a_hi = base + stage * STAGE_BYTES;
                         const uint32_t a_lo = a_hi + A_BYTES;
                         const uint32_t b_hi = a_hi + 2 * A_BYTES;
                         const uint32_t b_lo = b_hi + B_BYTES;
-                        const bool first_kb = (kb == ch * CHUNK_KB);
+                        const bool first_kb = (kb == c0);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint32_t off = k * UMMA_K * 4;
@@ -584,10 +291,10 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             umma_tf32(tmem_d, dah, dbl, kInstrDesc, 1u);
                             umma_tf32(tmem_d, dah, dbh, kInstrDesc, 1u);
                         }
-                        umma_commit(empty_bar(stage));
+                        umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs retire
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(tfull_bar(part));
+                    umma_commit(tfull_bar(part));        // partial sum complete
                     if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
                 }
             }
@@ -600,12 +307,12 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const int half = (warp - 4) >> 2;               // which 128-column half of the tile this warpgroup owns
         int part = 0;
         uint32_t part_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const TileCoord tc_ = LOWER ? raster_lower(tile) : raster(tile, tiles_m, tiles_n);
+        for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
+            const Unit w = unit_of<LOWER>(u, tiles_m, tiles_n, splits, k_blocks);
             float master[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) master[j] = 0.0f;
-            for (int ch = 0; ch < chunks; ++ch) {
+            for (int c0 = w.kb0; c0 < w.kb1; c0 += CHUNK_KB) {
                 mbar_wait(tfull_bar(part), part_phase);
                 fence_after();
 #pragma unroll
@@ -620,9 +327,9 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 if (lane == 0) mbar_arrive(tempty_bar(part));
                 if (++part == PARTIALS) { part = 0; part_phase ^= 1u; }
             }
-            const int64_t row = tc_.m_blk * BM + wq * 32 + lane;
-            const int64_t col0 = tc_.n_blk * BN + half * HALF;
-            if (row < M && col0 < N) {
+            const int64_t row = w.tile.m_blk * BM + wq * 32 + lane;
+            const int64_t col0 = w.tile.n_blk * BN + half * HALF;
+            if (row < M && col0 < N && w.kb1 > w.kb0) {
                 if (epi.vec_ok && col0 + HALF <= N) {
 #pragma unroll
                     for (int j = 0; j < HALF; j += 4) epi.vec4(row, col0 + j, master[j], master[j + 1], master[j + 2], master[j + 3]);
@@ -641,8 +348,6 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
-
-}  // namespace v3
 
 // ---- operand split -----------------------------------------------------------------------
 // hi/lo: [rows x Kp] with Kp = round_up(K, 32); padding columns are written as zeros.
@@ -719,15 +424,35 @@ inline size_t workspace_bytes(int64_t M, int64_t N, int64_t K)
     return (size_t)(M + N) * (size_t)Kp * sizeof(float) * 2 + 1024;
 }
 
-template <class Epi>
+// K splits of a product whose tile grid does not fill the chip a few times over (the train Gram Q_b^T Q_b:
+// 156 lower tiles at fraction 50 with K = 153 k): the split count that wastes the least of the last wave.
+inline int pick_splits(int64_t tiles, int k_blocks, int sms)
+{
+    if (tiles >= 4 * (int64_t)sms || k_blocks < 8 * CHUNK_KB) return 1;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= MAX_SPLITS; ++s) {
+        if (k_blocks / s < 4 * CHUNK_KB) break;
+        const int64_t units = tiles * s;
+        const double eff = (double)units / (double)(ceil_div(units, sms) * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+// `lower`: A == B (same pointer), only tiles touching the lower triangle are computed.  `EpiSplit` is the functor
+// used when K is split (it must ACCUMULATE atomically into a zero-initialised output); pass the same type as Epi
+// to forbid splitting.
+template <class Epi, class EpiSplit>
 static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                      const Epi &epi, void *workspace, size_t ws_bytes, cudaStream_t st, bool chunked = true,
-                      bool lower = false, bool wide = true)
+                      const Epi &epi, const EpiSplit *epi_split, void *workspace, size_t ws_bytes, cudaStream_t st,
+                      bool lower = false)
 {
     if (M <= 0 || N <= 0) return GNNGP_OK;
     GNNGP_REQUIRE(K > 0, "tcgen05 gemm: K must be positive");
     GNNGP_REQUIRE(M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31), "tcgen05 gemm: M/N exceed TMA coordinates");
-    const size_t need = workspace_bytes(M, N, K);
+    GNNGP_REQUIRE(!lower || (M == N && A == B && lda == ldb), "tcgen05 gemm: the lower-triangle mode needs A == B");
+    const size_t need = lower ? workspace_bytes(M, 0, K) : workspace_bytes(M, N, K);
     if (!workspace || ws_bytes < need) {
         set_error("tcgen05 gemm: workspace %zu < %zu bytes", ws_bytes, need);
         return GNNGP_ERR_WORKSPACE;
@@ -736,74 +461,49 @@ static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, 
     char *w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     float *a_hi = reinterpret_cast<float *>(w);
     float *a_lo = a_hi + M * Kp;
-    float *b_hi = a_lo + M * Kp;
-    float *b_lo = b_hi + N * Kp;
+    float *b_hi = lower ? a_hi : a_lo + M * Kp;
+    float *b_lo = lower ? a_lo : b_hi + N * Kp;
 
     const int threads = 256;
     const int max_blocks = sm_count() * 8;
     split_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M * (Kp / 4), threads), max_blocks), threads, 0, st>>>(A, lda, M, K, Kp, a_hi, a_lo);
     GNNGP_LAUNCHED();
-    split_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N * (Kp / 4), threads), max_blocks), threads, 0, st>>>(B, ldb, N, K, Kp, b_hi, b_lo);
-    GNNGP_LAUNCHED();
+    if (!lower) {                        // a symmetric product splits its one operand once
+        split_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N * (Kp / 4), threads), max_blocks), threads, 0, st>>>(B, ldb, N, K, Kp, b_hi, b_lo);
+        GNNGP_LAUNCHED();
+    }
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    const int bn = (chunked && !wide) ? v2::BN : BN;       // v3 and the unchunked kernel use 256-row B boxes
     if ((rc = make_map(&ma_hi, a_hi, M, Kp, BM)) != GNNGP_OK) return rc;
     if ((rc = make_map(&ma_lo, a_lo, M, Kp, BM)) != GNNGP_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, N, Kp, bn)) != GNNGP_OK) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, N, Kp, bn)) != GNNGP_OK) return rc;
-
-    if (chunked && wide) {
-        const int64_t tiles_m = ceil_div(M, v3::BM), tiles_n = ceil_div(N, v3::BN);
-        const int grid = (int)std::min<int64_t>(tiles_m * tiles_n, sm_count());
-        auto kernel3 = v3::gemm_nt_tc3_kernel<Epi, false>;
-        static bool configured3 = false;
-        if (!configured3) {
-            GNNGP_CUDA(cudaFuncSetAttribute(kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES));
-            configured3 = true;
-        }
-        kernel3<<<grid, v3::THREADS3, v3::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
-        GNNGP_LAUNCHED();
-        return GNNGP_OK;
-    }
-    if (chunked) {
-        const int64_t tiles_m = ceil_div(M, v2::BM), tiles_n = ceil_div(N, v2::BN);
-        if (lower) {      // symmetric product: only tiles on or below the diagonal are computed
-            GNNGP_REQUIRE(M == N, "tcgen05 gemm: the lower-triangle mode needs a square result");
-            const int grid = (int)std::min<int64_t>(tiles_m * (tiles_m + 1) / 2, sm_count());
-            auto kernel_l = v2::gemm_nt_tc2_kernel<Epi, true>;
-            static bool configured_l = false;
-            if (!configured_l) {
-                GNNGP_CUDA(cudaFuncSetAttribute(kernel_l, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
-                configured_l = true;
-            }
-            kernel_l<<<grid, THREADS, v2::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
-            GNNGP_LAUNCHED();
-            return GNNGP_OK;
-        }
-        const int grid = (int)std::min<int64_t>(tiles_m * tiles_n, sm_count());
-        auto kernel2 = v2::gemm_nt_tc2_kernel<Epi, false>;
-        static bool configured2 = false;
-        if (!configured2) {
-            GNNGP_CUDA(cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
-            configured2 = true;
-        }
-        kernel2<<<grid, THREADS, v2::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
-        GNNGP_LAUNCHED();
-        return GNNGP_OK;
-    }
+    if ((rc = make_map(&mb_hi, b_hi, N, Kp, BN)) != GNNGP_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, N, Kp, BN)) != GNNGP_OK) return rc;
 
     const int64_t tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
-    const int64_t total = tiles_m * tiles_n;
-    const int grid = (int)std::min<int64_t>(total, sm_count());
-    auto kernel = gemm_nt_tc_kernel<Epi>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-        GNNGP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
+    const int64_t tiles = lower ? lower_tile_count(tiles_m) : tiles_m * tiles_n;
+    const int k_blocks = (int)(Kp / BK);
+    const int splits = epi_split ? pick_splits(tiles, k_blocks, sm_count()) : 1;
+    const int grid = (int)std::min<int64_t>(tiles * splits, sm_count());
+    if (splits > 1) {
+        if (lower) {
+            auto kernel = gemm_nt_tc3_kernel<EpiSplit, true>;
+            GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
+            kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, splits, *epi_split);
+        } else {
+            auto kernel = gemm_nt_tc3_kernel<EpiSplit, false>;
+            GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
+            kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, splits, *epi_split);
+        }
+    } else if (lower) {
+        auto kernel = gemm_nt_tc3_kernel<Epi, true>;
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
+        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, epi);
+    } else {
+        auto kernel = gemm_nt_tc3_kernel<Epi, false>;
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
+        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, epi);
     }
-    kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, (int)(Kp / BK), tiles_m, tiles_n, epi);
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }

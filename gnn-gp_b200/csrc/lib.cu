@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <atomic>
 #include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -34,6 +36,20 @@ int sm_count()
     return cached[dev];
 }
 
+cudaError_t ensure_dynamic_smem(const void *kernel, int bytes)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kernel, dev})) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err == cudaSuccess) done.insert({kernel, dev});
+    return err;
+}
+
 }  // namespace gnngp
 
 extern "C" {
@@ -58,7 +74,7 @@ int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor
 
 int gnngp_set_gemm_engine(int engine)
 {
-    if (engine < 0 || engine > 4) engine = 2;
+    if (engine < 0 || engine > 2) engine = 2;
     return gnngp::g_gemm_engine.exchange(engine);
 }
 

@@ -485,11 +485,7 @@ int gnngp_argmax_count(const float *fitted, const int64_t *y, const uint8_t *mem
     cudaStream_t st = as_stream(stream);
     GNNGP_CUDA(cudaMemsetAsync(counts, 0, (size_t)G * 8 * sizeof(int32_t), st));
     if (C <= 96) {
-        static bool configured = false;
-        if (!configured) {
-            GNNGP_CUDA(cudaFuncSetAttribute(argmax_count_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 * 4));
-            configured = true;
-        }
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(argmax_count_tiled_kernel), 256 * 96 * 4));
         argmax_count_tiled_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)G), 256, (size_t)256 * C * sizeof(float), st>>>(
             fitted, y, membership, n, (int)C, counts);
         GNNGP_LAUNCHED();

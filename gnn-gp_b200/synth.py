@@ -39,6 +39,9 @@ SHAPES: Dict[str, dict] = {
     "tiny": dict(n=257, und=1100, f=40, c=4, split=(120, 60, 77), feat="gauss", sep=0.3, p_same=0.5),
     "tiny-reg": dict(n=203, und=900, f=24, c=0, split=(100, 50, 53), feat="gauss", sep=0.5, p_same=0.6),
     "small": dict(n=1500, und=12000, f=96, c=5, split=(700, 300, 500), feat="gauss", sep=0.15, p_same=0.5),
+    # smoke(): the smallest graph on which the auto dispatch takes the production kernels — dense rows (average degree
+    # ~84) and >= 256 operand columns for the panel SpMM, >= 64 output tiles for the tcgen05 contractions
+    "smoke": dict(n=6000, und=250000, f=300, c=5, split=(2400, 1200, 2400), feat="gauss", sep=0.15, p_same=0.5),
 }
 
 

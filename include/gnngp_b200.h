@@ -42,8 +42,7 @@ const char *gnngp_last_error(void);
 int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor);
 /* Dense-contraction engine: 0 = fp32 CUDA-core tiles, 1 = tcgen05 3xTF32 with chunked accumulation
  * (TMA + TMEM; 128x256 tiles, two epilogue warpgroups), 2 = auto (tcgen05 when the shape fills the tile
- * grid), 3 = the unchunked 128x256 tcgen05 kernel (biased accumulation; measurement only), 4 = the chunked
- * 128x128 tcgen05 kernel (measurement only).  Returns the previous setting. */
+ * grid).  Returns the previous setting. */
 int gnngp_set_gemm_engine(int engine);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gnngp_launch_count(void);

@@ -38,7 +38,7 @@ for label, M, N, K, positive in (("rand K=3107", 2048, 1024, 3107, False), ("pos
     b = torch.rand(N, K, device=dev, generator=g) if positive else torch.randn(N, K, device=dev, generator=g)
     want = a.double() @ b.double().T
     row = {"torch_fp32": rel(a @ b.T, want)}
-    for engine, name in ((0, "simt"), (1, "tc_v3_chunked_128x256"), (4, "tc_v2_chunked_128x128"), (3, "tc_v1_unchunked")):
+    for engine, name in ((0, "simt"), (1, "tc3_chunked_128x256")):
         ops.set_gemm_engine(engine)
         row[name] = rel(ops.gemm_nt(a, b), want)
     out["accuracy " + label] = row
@@ -56,12 +56,13 @@ bt = torch.randn(G * C, m, device=dev, generator=g)
 qbt = torch.randn(m, nt, device=dev, generator=g)
 e = ops.empty(n, na, dev)
 fitted = torch.empty((G, n, C), device=dev)
-for engine, name in ((1, "tc_v3_chunked_128x256"), (4, "tc_v2_chunked_128x128"), (3, "tc_v1_unchunked")):
+for engine, name in ((1, "tc3_chunked_128x256"),):
     ops.set_gemm_engine(engine)
     row = {}
     row["gram_arccos %dx%dx%d" % (n, na, m)] = timeit(lambda: ops.gram_arccos(q, l, s, t, out=e))
     row["backproject %dx%dx%d" % (n, na, na)] = timeit(lambda: ops.gemm_nt(e, wt))
     row["train_gram %dx%dx%d" % (m, m, nt)] = timeit(lambda: ops.gemm_nt(qbt, qbt))
+    row["train_syrk_lower_splitk %dx%dx%d" % (m, m, nt)] = timeit(lambda: ops.syrk(qbt))
     row["nugget_sweep %dx%dx%d" % (n, G * C, m)] = timeit(lambda: ops.nugget_sweep(q, bt, G, C, out=fitted))
     row["nugget_sweep_as_plain_gemm"] = timeit(lambda: ops.gemm_nt(q, bt))
     row["nugget_sweep C=40"] = timeit(lambda: ops.nugget_sweep(q, bt[:G * 40], G, 40, out=fitted.view(-1)[:G * n * 40].view(G, n, 40)))
