@@ -29,6 +29,9 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gnngp {
@@ -169,35 +172,39 @@ __device__ __forceinline__ TileCoord raster(int64_t tile, int64_t tiles_m, int64
     return t;
 }
 
-// Tiles of a symmetric product that touch the lower triangle.  A 128 x 256 tile (i, j) does when 256 j <= 128 i + 127,
-// i.e. j <= i / 2: row-blocks 2p and 2p+1 have p + 1 tiles each, p (p + 1) tiles precede the pair.
-__host__ __device__ inline int64_t lower_tile_count(int64_t tiles_m)
+// Symmetric products: only tiles that touch the lower triangle are computed.  A 128 x 256 tile (i, j) does when
+// 256 j <= 128 i + 127, i.e. j <= i / 2.  The host lists the live tiles (into the workspace) in SUPER-ROWS of 16
+// row-blocks, each walked column by column: 16 consecutive units share one B panel, and the ~148 units in flight
+// share 16 A panels and ~9 B panels through the L2 — with a row-by-row walk every unit streamed its own 256-row
+// panel of a K = 153 k operand from HBM and the train Gram ran HBM-bound.
+inline void lower_tile_list(int64_t tiles_m, std::vector<int2> &out)
 {
-    const int64_t p = tiles_m / 2;
-    return p * (p + 1) + ((tiles_m & 1) ? p + 1 : 0);
-}
-__device__ __forceinline__ TileCoord raster_lower(int64_t t)
-{
-    int64_t p = (int64_t)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((p + 1) * (p + 2) <= t) ++p;
-    while (p * (p + 1) > t) --p;
-    const int64_t r = t - p * (p + 1);
-    TileCoord c;
-    if (r <= p) { c.m_blk = 2 * p; c.n_blk = r; }
-    else { c.m_blk = 2 * p + 1; c.n_blk = r - (p + 1); }
-    return c;
+    out.clear();
+    for (int64_t r0 = 0; r0 < tiles_m; r0 += 16) {
+        const int64_t r1 = std::min<int64_t>(tiles_m, r0 + 16);
+        for (int64_t j = 0; j <= ((r1 - 1) >> 1); ++j)
+            for (int64_t i = std::max<int64_t>(r0, 2 * j); i < r1; ++i) out.push_back(make_int2((int)i, (int)j));
+    }
 }
 
-// Work unit u = (tile, K split): tile = u / splits, this unit contracts k-blocks [kb0, kb1).
+// Work unit u = (K split, tile slot): split-major, so that the units in flight contract the same K range and
+// share operand panels; this unit contracts k-blocks [kb0, kb1) (empty for an unused slot).
 struct Unit { TileCoord tile; int kb0, kb1; };
 template <bool LOWER>
-__device__ __forceinline__ Unit unit_of(int64_t u, int64_t tiles_m, int64_t tiles_n, int splits, int k_blocks)
+__device__ __forceinline__ Unit unit_of(int64_t u, int64_t slots, int64_t tiles_m, int64_t tiles_n, int splits, int k_blocks,
+                                        const int2 *__restrict__ tile_list)
 {
-    const int64_t t = u / splits;
-    const int sp = (int)(u - t * splits);
+    const int sp = (int)(u / slots);
+    const int64_t t = u - (int64_t)sp * slots;
     const int per = (k_blocks + splits - 1) / splits;
     Unit w;
-    w.tile = LOWER ? raster_lower(t) : raster(t, tiles_m, tiles_n);
+    if (LOWER) {
+        const int2 c = __ldg(tile_list + t);
+        w.tile.m_blk = c.x;
+        w.tile.n_blk = c.y;
+    } else {
+        w.tile = raster(t, tiles_m, tiles_n);
+    }
     w.kb0 = min(k_blocks, sp * per);
     w.kb1 = min(k_blocks, w.kb0 + per);
     return w;
@@ -207,7 +214,8 @@ template <class Epi, bool LOWER>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, int splits, Epi epi)
+                   int64_t M, int64_t N, int k_blocks, int64_t tiles_m, int64_t tiles_n, int splits, const int2 *tile_list,
+                   int64_t slots, Epi epi)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -234,7 +242,7 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t total = (LOWER ? lower_tile_count(tiles_m) : tiles_m * tiles_n) * splits;
+    const int64_t total = slots * splits;
 
     // Register re-balancing is warpgroup-wide and scoped like in the CUTLASS warp-specialised kernels: the
     // control warpgroup shrinks to 40 registers at the top of ITS branch, the epilogue warpgroups grow to 232
@@ -247,7 +255,7 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
-                const Unit w = unit_of<LOWER>(u, tiles_m, tiles_n, splits, k_blocks);
+                const Unit w = unit_of<LOWER>(u, slots, tiles_m, tiles_n, splits, k_blocks, tile_list);
                 const int32_t m0 = (int32_t)(w.tile.m_blk * BM), n0 = (int32_t)(w.tile.n_blk * BN);
                 for (int kb = w.kb0; kb < w.kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -267,7 +275,7 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             int stage = 0, part = 0;
             uint32_t phase = 0, part_phase = 0;
             for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
-                const Unit w = unit_of<LOWER>(u, tiles_m, tiles_n, splits, k_blocks);
+                const Unit w = unit_of<LOWER>(u, slots, tiles_m, tiles_n, splits, k_blocks, tile_list);
                 for (int c0 = w.kb0; c0 < w.kb1; c0 += CHUNK_KB) {
                     mbar_wait(tempty_bar(part), part_phase ^ 1u);
                     fence_after();
@@ -308,7 +316,7 @@ gemm_nt_tc3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         int part = 0;
         uint32_t part_phase = 0;
         for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
-            const Unit w = unit_of<LOWER>(u, tiles_m, tiles_n, splits, k_blocks);
+            const Unit w = unit_of<LOWER>(u, slots, tiles_m, tiles_n, splits, k_blocks, tile_list);
             float master[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) master[j] = 0.0f;
@@ -421,7 +429,9 @@ inline int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t Kp
 inline size_t workspace_bytes(int64_t M, int64_t N, int64_t K)
 {
     const int64_t Kp = round_up(K > 0 ? K : 1, BK);
-    return (size_t)(M + N) * (size_t)Kp * sizeof(float) * 2 + 1024;
+    const int64_t tm = ceil_div(M > 0 ? M : 1, BM);
+    // hi/lo operand copies + (symmetric products) the list of live tiles
+    return (size_t)(M + N) * (size_t)Kp * sizeof(float) * 2 + (size_t)(tm * (tm / 2 + 2)) * sizeof(int2) + 2048;
 }
 
 // K splits of a product whose tile grid does not fill the chip a few times over (the train Gram Q_b^T Q_b:
@@ -481,28 +491,40 @@ static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, 
     if ((rc = make_map(&mb_lo, b_lo, N, Kp, BN)) != GNNGP_OK) return rc;
 
     const int64_t tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
-    const int64_t tiles = lower ? lower_tile_count(tiles_m) : tiles_m * tiles_n;
+    int64_t slots = tiles_m * tiles_n;
+    const int2 *tile_list = nullptr;
+    if (lower) {
+        std::vector<int2> live;
+        lower_tile_list(tiles_m, live);
+        slots = (int64_t)live.size();
+        // the list lives behind the operand copies in the caller's workspace
+        int2 *dst = reinterpret_cast<int2 *>((reinterpret_cast<uintptr_t>(b_lo + N * Kp) + 255) & ~(uintptr_t)255);
+        GNNGP_REQUIRE(reinterpret_cast<char *>(dst + slots) <= reinterpret_cast<char *>(workspace) + ws_bytes,
+                      "tcgen05 gemm: workspace too small for the tile list");
+        GNNGP_CUDA(cudaMemcpyAsync(dst, live.data(), live.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        tile_list = dst;
+    }
     const int k_blocks = (int)(Kp / BK);
-    const int splits = epi_split ? pick_splits(tiles, k_blocks, sm_count()) : 1;
-    const int grid = (int)std::min<int64_t>(tiles * splits, sm_count());
+    const int splits = epi_split ? pick_splits(slots, k_blocks, sm_count()) : 1;
+    const int grid = (int)std::min<int64_t>(slots * splits, sm_count());
     if (splits > 1) {
         if (lower) {
             auto kernel = gemm_nt_tc3_kernel<EpiSplit, true>;
             GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
-            kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, splits, *epi_split);
+            kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, splits, tile_list, slots, *epi_split);
         } else {
             auto kernel = gemm_nt_tc3_kernel<EpiSplit, false>;
             GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
-            kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, splits, *epi_split);
+            kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, splits, tile_list, slots, *epi_split);
         }
     } else if (lower) {
         auto kernel = gemm_nt_tc3_kernel<Epi, true>;
         GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
-        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, epi);
+        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, tile_list, slots, epi);
     } else {
         auto kernel = gemm_nt_tc3_kernel<Epi, false>;
         GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), SMEM_BYTES));
-        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, epi);
+        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, tile_list, slots, epi);
     }
     GNNGP_LAUNCHED();
     return GNNGP_OK;

@@ -61,6 +61,12 @@ def test_cli_metrics_match_the_oracle_on_the_same_graph(capsys, argv, shape, fra
     ref = orc.run(data.x.cpu().numpy(), data.y.cpu().numpy(), data.edge_index[0].cpu().numpy(), data.edge_index[1].cpu().numpy(),
                   data.edge_attr.cpu().numpy(), masks, torch.logspace(-3, 1, 101).numpy(), layers=2, sigma_b=0.0, sigma_w=1.0,
                   nystrom=bool(fraction), method="GCN")
+    # the selected nugget is an argmax over a curve with exact ties (accuracies are multiples of 1/size): the best
+    # validation value must agree, and the printed triple must be the oracle's triple at one of the grid's nuggets
+    tol = {key: 2.5 / int(masks[key].sum()) + 1e-6 for key in ("train", "val", "test")}
+    assert abs(float(table[0, 2]) - float(ref["summary"]["val"])) <= tol["val"], (float(table[0, 2]), ref["summary"]["val"])
+    curves = {key: np.asarray(ref["result"][key], dtype=np.float64) for key in ("train", "val", "test")}
+    close = np.ones(101, dtype=bool)
     for col, key in ((1, "train"), (2, "val"), (3, "test")):
-        size = int(masks[key].sum())
-        assert abs(float(table[0, col]) - float(ref["summary"][key])) <= 2.5 / size + 1e-6, (key, float(table[0, col]), ref["summary"][key])
+        close &= np.abs(curves[key] - float(table[0, col])) <= tol[key]
+    assert close.any(), ("no nugget of the oracle's grid reproduces the CLI's line", [float(v) for v in table[0]], ref["summary"])
