@@ -170,14 +170,18 @@ def rel_fro(a, b) -> float:
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def collect_samples(model, sample_idx, row_idx, best=None) -> dict:
-    """Small samples of a finished single-GPU run: Q Qᵀ block, posterior-mean rows, all argmax predictions, curves."""
-    q = model.Q[sample_idx].double()
-    curves = {k: v.numpy() for k, v in model.result.items()}
+def collect_samples(model, sample_idx, row_idx, best=None, fit=None, ksamp=None, curves=None) -> dict:
+    """Small samples of a finished single-GPU run: Q Qᵀ block, posterior-mean rows, all argmax predictions, curves.
+    ``best`` = the nugget index to sample at (the REFERENCE's selected nugget when comparing with a reference run)."""
+    if ksamp is None:
+        q = model.Q[sample_idx].double()
+        ksamp = (q @ q.T).cpu().numpy()
+    if curves is None:
+        curves = {k: v.numpy() for k, v in model.result.items()}
     if best is None:
         best = int(np.argmax(curves["val"]))
-    fit = model.fit
-    return {"ksamp": (q @ q.T).cpu().numpy(), "best": best, "fit_best": fit[best][row_idx].cpu().numpy(),
+    fit = model.fit if fit is None else fit
+    return {"ksamp": ksamp, "best": best, "fit_best": fit[best][row_idx].cpu().numpy(),
             "fit_mid": fit[50][row_idx].cpu().numpy(), "pred_best": torch.argmax(fit[best], 1).cpu().numpy(), "curves": curves}
 
 
@@ -453,7 +457,14 @@ def run_ours(args):
     n = info["nodes"]
     sample_idx = torch.from_numpy(cases.sample_index(n, args.seed)).to(dev)
     row_idx = torch.from_numpy(cases.big_row_sample(n, args.seed)).to(dev)
-    ours_headline = collect_samples(model, sample_idx, row_idx) if world == 1 else None
+    # kept for the live comparison with the reference's own run further down (sampled at ITS selected nugget):
+    # the posterior means [G, N, C] (3.9 GB), the sampled Q Q^T block and the metric curves
+    ours_headline = None
+    if world == 1:
+        q_s = model.Q[sample_idx].double()
+        ours_headline = {"fit": model.fit, "ksamp": (q_s @ q_s.T).cpu().numpy(), "curves": {k: v.numpy() for k, v in model.result.items()},
+                         "best": int(np.argmax(model.result["val"].numpy()))}
+        del q_s
 
     # ---- fraction-50 point of the landmark sweep (figure4.sh:2) + parity against the reference's golden fixture
     sweep = None
@@ -564,14 +575,16 @@ def run_ours(args):
             gpu_ref, ref_samples = ref_arm.gpu_reference_full(data, land, nugget, args.layers, args.sigma_b, args.sigma_w,
                                                               sample_idx, row_idx, steps=1)
             if ref_samples is not None:
-                # compare at the REFERENCE's selected nugget
-                if ours_headline["best"] != ref_samples["best"]:
-                    gpu_ref["best_nugget_index_differs"] = [ours_headline["best"], ref_samples["best"]]
-                else:
-                    ref_samples["fit_scale"] = float(np.abs(ref_samples["fit_best"]).max())
-                    parity_live = parity_record(ours_headline, ref_samples, "live: unmodified reference (baseline/_ref) on this GPU, "
-                                                                            "same inputs, fraction %d" % args.fraction)
+                # compare at the REFERENCE's selected nugget (validation accuracy is flat over the small nuggets, so
+                # the two argmax-over-ties can land on different indices of the same plateau)
+                gpu_ref["selected_nugget_index"] = {"ours": ours_headline["best"], "reference": ref_samples["best"]}
+                ref_samples["fit_scale"] = float(np.abs(ref_samples["fit_best"]).max())
+                ours_at = collect_samples(None, sample_idx, row_idx, best=ref_samples["best"], fit=ours_headline["fit"],
+                                          ksamp=ours_headline["ksamp"], curves=ours_headline["curves"])
+                parity_live = parity_record(ours_at, ref_samples, "live: unmodified reference (baseline/_ref) on this GPU, "
+                                                                  "same inputs, fraction %d" % args.fraction)
                 gpu_ref["speedup_value"] = round(gpu_ref["value"] / seconds, 2)
+            ours_headline = None
         except Exception as exc:
             gpu_ref = {"unavailable": "gpu reference failed: %r" % (exc,)}
         torch.cuda.empty_cache()

@@ -1,0 +1,722 @@
+// K9 — the GP posterior solve for ALL nuggets without an eigendecomposition.
+//
+// Replaces the `torch.linalg.eigh(Q[mb].T @ Q[mb])` + 101 x (`v @ (temp / (w + eps d))`) of the reference's
+// fit_Nystrom (src/predict.py:57-62).  `V diag(1 / (w + eps d)) V^T` IS `(G + eps d I)^-1` with G = Q_b^T Q_b, so
+// what the 101 nuggets need is 101 SHIFTED SOLVES with one matrix — not its eigenvectors.  cuSOLVER's `syevd`
+// spends 94 % of its time in a one-stage tridiagonalisation whose symmetric matrix-vector products are bound by
+// HBM / L2 bandwidth (2.3 s at m = 15 405, 56 ms at m = 3 053 on B200).  Here:
+//
+//   1. G (fp32, lower triangle valid) -> symmetric fp64 copy A.
+//   2. successive band reduction  A = Q1 B Q1^T  to bandwidth b = 128 (Bischof/Lang/Sun stage 1): per panel a
+//      Householder QR of the block below the band (`sbr_panel_kernel`, a cooperative grid holding the panel in
+//      shared memory, ONE grid barrier per column) and a two-sided block-reflector update of the trailing matrix
+//      in GEMM form (`dgemm_kernel`): Y = A22 V, W = Y T - 1/2 V (T^T V^T Y T), A22 -= V W^T + W V^T.  BLAS-3,
+//      2 m^3 flops in fp64, no bulge chasing, no tridiagonal eigensolver.
+//   3. rhs <- Q1^T rhs (block reflectors in GEMM form).
+//   4. per nugget one CTA: banded Cholesky of B + shift I in a sliding shared-memory window fused with the
+//      forward substitution, then the backward substitution (`band_cholesky_solve_kernel`), 41 right-hand sides.
+//   5. solutions <- Q1 solutions, written as the fp32 coefficient block [(G*C) x m] the sweep contraction consumes.
+//
+// Everything is fp64 (the nugget 1e-3 d sits ~1e-8 below the largest eigenvalue of G; fp32 would not resolve it).
+// A non-positive pivot (rounding noise of the fp32 Gram above the smallest shift) is counted in `info`; the caller
+// then falls back to the eigen route, which tolerates an indefinite matrix.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gnngp {
+namespace bandfit {
+
+constexpr int BW = 128;                 // bandwidth of the reduced matrix = panel width
+constexpr int LDP = BW + 1;             // padded slab row (bank-conflict-free column walks)
+
+// ---------------------------------------------------------------------------------------------
+// generic fp64 GEMM on CUDA cores:  C = alpha * (A1 B1 + A2 B2) + beta * C   (or atomic accumulation for split-K)
+// operands are strided views: A(i, k) = p[i * rs + k * cs], B(k, j) = p[k * rs + j * cs]; one of the two strides
+// of every operand is 1.  128 x 64 tiles, K steps of 16, 8 x 4 accumulators per thread, register prefetch.
+// ---------------------------------------------------------------------------------------------
+struct View { const double *p; int64_t rs, cs; };
+
+constexpr int GM = 128, GN = 64, GK = 16;
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(256, 2)
+dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1, View B1, View A2, View B2, double beta,
+             double *__restrict__ C, int64_t ldc, int splits)
+{
+    __shared__ __align__(16) double As[GK][GM + 2];
+    __shared__ __align__(16) double Bs[GK][GN + 2];
+    const int t = threadIdx.x;
+    const int tx = t & 15, ty = t >> 4;                     // 16 x 16 threads: 4 columns x 8 rows each
+    const int64_t m0 = (int64_t)blockIdx.y * GM, n0 = (int64_t)blockIdx.x * GN;
+    const int64_t tiles1 = (K1 + GK - 1) / GK, tiles2 = (K2 + GK - 1) / GK;
+    const int64_t tiles = tiles1 + tiles2;
+    const int64_t per = (tiles + splits - 1) / splits;
+    const int64_t t_begin = (int64_t)blockIdx.z * per, t_end = min(tiles, t_begin + per);
+    if (t_begin >= t_end) return;
+
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    double ra[8], rb[4];
+    auto fetch = [&](int64_t kt) {
+        const bool second = kt >= tiles1;
+        const View A = second ? A2 : A1, B = second ? B2 : B1;
+        const int64_t K = second ? K2 : K1;
+        const int64_t k0 = (second ? kt - tiles1 : kt) * GK;
+        if (A.cs == 1) {                                    // k-contiguous rows
+            const int kk = t & 15;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int64_t row = m0 + (t >> 4) + 16 * r;
+                ra[r] = (row < M && k0 + kk < K) ? __ldg(A.p + row * A.rs + (k0 + kk)) : 0.0;
+            }
+        } else {                                            // m-contiguous columns
+            const int mm = t & 127;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int64_t kk = (t >> 7) + 2 * r;
+                ra[r] = (m0 + mm < M && k0 + kk < K) ? __ldg(A.p + (m0 + mm) * A.rs + (k0 + kk) * A.cs) : 0.0;
+            }
+        }
+        if (B.cs == 1) {                                    // n-contiguous rows of B
+            const int jj = t & 63;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t kk = (t >> 6) + 4 * r;
+                rb[r] = (n0 + jj < N && k0 + kk < K) ? __ldg(B.p + (k0 + kk) * B.rs + (n0 + jj)) : 0.0;
+            }
+        } else {                                            // k-contiguous (B given as rows of B^T)
+            const int kk = t & 15;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t jj = (t >> 4) + 16 * r;
+                rb[r] = (n0 + jj < N && k0 + kk < K) ? __ldg(B.p + (k0 + kk) * B.rs + (n0 + jj) * B.cs) : 0.0;
+            }
+        }
+    };
+    auto stash = [&](int64_t kt) {
+        const bool second = kt >= tiles1;
+        const View A = second ? A2 : A1, B = second ? B2 : B1;
+        if (A.cs == 1) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) As[t & 15][(t >> 4) + 16 * r] = ra[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) As[(t >> 7) + 2 * r][t & 127] = ra[r];
+        }
+        if (B.cs == 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) Bs[(t >> 6) + 4 * r][t & 63] = rb[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) Bs[t & 15][(t >> 4) + 16 * r] = rb[r];
+        }
+    };
+
+    fetch(t_begin);
+    for (int64_t kt = t_begin; kt < t_end; ++kt) {
+        __syncthreads();
+        stash(kt);
+        __syncthreads();
+        if (kt + 1 < t_end) fetch(kt + 1);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(&As[kk][ty * 8 + i]);
+                a[i] = v.x; a[i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(&Bs[kk][tx * 4 + j]);
+                b[j] = v.x; b[j + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t row = m0 + ty * 8 + i;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = n0 + tx * 4 + j;
+            if (col >= N) continue;
+            double *c = C + row * ldc + col;
+            if (ATOMIC) atomicAdd(c, alpha * acc[i][j]);
+            else *c = (beta == 0.0) ? alpha * acc[i][j] : fma(beta, *c, alpha * acc[i][j]);
+        }
+    }
+}
+
+static const View kNoView = {nullptr, 0, 0};
+
+// C = alpha (A1 B1 + A2 B2) + beta C; splits > 1 accumulates atomically into C (the caller zeroed it; beta unused)
+static int dgemm(int64_t M, int64_t N, int64_t K1, View A1, View B1, int64_t K2, View A2, View B2, double alpha, double beta,
+                 double *C, int64_t ldc, int splits, cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return GNNGP_OK;
+    const dim3 grid((unsigned)ceil_div(N, GN), (unsigned)ceil_div(M, GM), (unsigned)std::max(1, splits));
+    if (splits > 1) dgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K1, K2, alpha, A1, B1, A2, B2, beta, C, ldc, splits);
+    else dgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K1, K2, alpha, A1, B1, A2, B2, beta, C, ldc, 1);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+
+// K splits that give a small output a chip's worth of CTAs
+static int splits_for(int64_t M, int64_t N, int64_t K)
+{
+    const int64_t tiles = ceil_div(M, GM) * ceil_div(N, GN);
+    const int64_t ktiles = ceil_div(K, GK);
+    int64_t s = std::min<int64_t>(ktiles / 4, (2 * (int64_t)sm_count()) / std::max<int64_t>(tiles, 1));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(s, 512));
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 Gram (lower triangle valid) -> full symmetric fp64 matrix
+// ---------------------------------------------------------------------------------------------
+__global__ void symmetrize_kernel(const float *__restrict__ G, int64_t ldg, int64_t m, double *__restrict__ A, int64_t lda)
+{
+    const int64_t total = m * m, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / m, c = i - r * m;
+        A[r * lda + c] = (double)(r >= c ? __ldg(G + r * ldg + c) : __ldg(G + c * ldg + r));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid-wide barrier for the cooperative panel kernel (monotone counter; bounded spin -> trap, never a hang)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int n_ctas, unsigned int &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += n_ctas;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const long long t0 = clock64();
+        while (true) {
+            unsigned int seen;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if ((int)(seen - target) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) {
+                printf("gnngp band fit: grid barrier timed out (block %d)\n", blockIdx.x);
+                __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Householder QR of one s x BW panel (the block below the band), cooperative grid.
+//
+// CTA c keeps rows [c * rows_per, ...) of the panel in shared memory for the whole factorisation.  Column step k:
+//   pass 1   every CTA adds its part of  g[c] = sum_{i >= k} P[i][c] * P[i][k]  (ALL columns c at once) to a global
+//            vector; CTA 0 (which owns the top BW rows, hence row k) also publishes row k.          -> ONE barrier
+//   pass 2   g[k] = |x|^2 gives the reflector (alpha, v0, tau); w = P^T v follows from g and row k WITHOUT a second
+//            reduction because v = (x - alpha e_1) / v0 differs from x in one entry: w[c] = (g[c] - alpha P[k][c]) / v0.
+//            Each CTA applies  P[i][c] -= tau v_i w[c]  (c > k) to its rows and overwrites column k with v.
+// The reduction vectors are triple-buffered: buffer (k+1) % 3 is cleared in step k, two barriers after its last read.
+// Output: V (explicit unit lower trapezoidal, s x BW, row-major), R (BW x BW upper triangle), tau (BW).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+sbr_panel_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows_per, double *__restrict__ V, double *__restrict__ R,
+                 double *__restrict__ tau_out, double *__restrict__ gbuf /*3 x BW*/, double *__restrict__ rowk /*3 x BW*/,
+                 unsigned int *counter)
+{
+    extern __shared__ double slab[];                        // rows_per x LDP
+    __shared__ double w_s[BW];
+    __shared__ double red[2][BW];
+    __shared__ double hh[4];                                // alpha, v0, tau, live flag
+    const int t = threadIdx.x;
+    const int c = t & (BW - 1), h = t >> 7;                 // column, half (two halves split the slab's rows)
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per;
+    const int nrows = (int)max((int64_t)0, min((int64_t)rows_per, s - row0));
+    unsigned int target = 0;
+
+    for (int i = h; i < nrows; i += 2) slab[i * LDP + c] = Ap[(row0 + i) * lda + c];
+    if (blockIdx.x == 0)
+        for (int i = t; i < 3 * BW; i += blockDim.x) gbuf[i] = 0.0;   // all three reduction buffers start clean
+    const int steps = (int)min((int64_t)BW, s);
+    grid_barrier(counter, gridDim.x, target);
+
+    for (int k = 0; k < steps; ++k) {
+        double *g = gbuf + (k % 3) * BW;
+        double *rk = rowk + (k % 3) * BW;
+        // ---- pass 1: partial dots of column k (rows >= k) with every column
+        {
+            const int lo = (int)max((int64_t)0, (int64_t)k - row0);       // first local row with global index >= k
+            double part = 0.0;
+            for (int i = lo + h; i < nrows; i += 2) part = fma(slab[i * LDP + c], slab[i * LDP + k], part);
+            red[h][c] = part;
+            __syncthreads();
+            if (h == 0) {
+                const double sum = red[0][c] + red[1][c];
+                if (nrows > lo) atomicAdd(g + c, sum);
+                if (blockIdx.x == 0) {
+                    rk[c] = slab[k * LDP + c];                             // row k lives in CTA 0 (k < BW <= rows_per)
+                    gbuf[((k + 1) % 3) * BW + c] = 0.0;
+                }
+            }
+        }
+        grid_barrier(counter, gridDim.x, target);
+        // ---- pass 2: reflector + rank-1 update of this CTA's rows
+        if (t == 0) {
+            const double nrm2 = __ldcg(g + k), x0 = __ldcg(rk + k);
+            if (!(nrm2 > 0.0)) { hh[0] = x0; hh[1] = 1.0; hh[2] = 0.0; hh[3] = 0.0; }     // zero column: H = I
+            else {
+                const double nrm = sqrt(nrm2);
+                const double alpha = x0 >= 0.0 ? -nrm : nrm;
+                hh[0] = alpha; hh[1] = x0 - alpha; hh[2] = (alpha - x0) / alpha; hh[3] = 1.0;
+            }
+        }
+        __syncthreads();
+        const double alpha = hh[0], v0 = hh[1], tau = hh[2];
+        const bool live = hh[3] != 0.0;
+        if (h == 0) w_s[c] = live ? (__ldcg(g + c) - alpha * __ldcg(rk + c)) / v0 : 0.0;
+        __syncthreads();
+        if (live) {
+            const double wc = w_s[c];
+            const int lo = (int)max((int64_t)0, (int64_t)k + 1 - row0);   // rows strictly below row k
+            if (c > k) {
+                for (int i = lo + h; i < nrows; i += 2) {
+                    const double vi = slab[i * LDP + k] / v0;
+                    slab[i * LDP + c] = fma(-tau * vi, wc, slab[i * LDP + c]);
+                }
+                if (blockIdx.x == 0 && h == 0) slab[k * LDP + c] = fma(-tau, wc, slab[k * LDP + c]);   // row k: v_k = 1
+            }
+            __syncthreads();
+            if (c == k) {
+                for (int i = lo + h; i < nrows; i += 2) slab[i * LDP + k] /= v0;
+                if (blockIdx.x == 0 && h == 0) slab[k * LDP + k] = alpha;
+            }
+        }
+        if (blockIdx.x == 0 && t == 0) tau_out[k] = tau;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0)
+        for (int k = steps + t; k < BW; k += blockDim.x) tau_out[k] = 0.0;
+    // ---- write V (explicit) and R
+    for (int i = h; i < nrows; i += 2) {
+        const int64_t gi = row0 + i;
+        double v = slab[i * LDP + c];
+        if (c >= steps) v = 0.0;
+        else if (gi < c) v = 0.0;
+        else if (gi == c) v = 1.0;
+        V[gi * BW + c] = v;
+        if (gi < BW) R[gi * BW + c] = (gi <= c && gi < steps) ? slab[i * LDP + c] : 0.0;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t gi = s + h; gi < BW; gi += 2) R[gi * BW + c] = 0.0;     // panels shorter than BW rows
+}
+
+// T of the compact WY form from V^T V and tau (LAPACK dlarft, forward columnwise):  T[:k, k] = -tau_k T[:k, :k] (V^T V)[:k, k]
+__global__ void __launch_bounds__(BW, 1)
+larft_kernel(const double *__restrict__ VtV, const double *__restrict__ tau, double *__restrict__ T)
+{
+    extern __shared__ double Ts[];                          // BW x LDP
+    __shared__ double z[BW];
+    const int r = threadIdx.x;
+    for (int cidx = 0; cidx < BW; ++cidx) Ts[r * LDP + cidx] = 0.0;
+    __syncthreads();
+    for (int k = 0; k < BW; ++k) {
+        const double tk = tau[k];
+        z[r] = (r < k) ? VtV[r * BW + k] : 0.0;
+        __syncthreads();
+        if (r < k) {
+            double sum = 0.0;
+            for (int j = r; j < k; ++j) sum = fma(Ts[r * LDP + j], z[j], sum);   // upper triangular T[:k, :k]
+            Ts[r * LDP + k] = -tk * sum;
+        } else if (r == k) {
+            Ts[r * LDP + k] = tk;
+        }
+        __syncthreads();
+    }
+    for (int cidx = 0; cidx < BW; ++cidx) T[r * BW + cidx] = Ts[r * LDP + cidx];
+}
+
+// band storage Bd[j][k] = A[j + k][j], k = 0..BW, for the BW columns that start at j0 (diagonal block from A,
+// the rows below it from R); `have_r` = 0 for the last, unreduced block
+__global__ void band_extract_kernel(const double *__restrict__ A, int64_t lda, int64_t m, int64_t j0, const double *__restrict__ R,
+                                    int have_r, double *__restrict__ Bd)
+{
+    const int jj = blockIdx.x;                              // column within the block
+    const int64_t j = j0 + jj;
+    if (j >= m) return;
+    const int64_t r0 = j0 + BW;
+    for (int k = threadIdx.x; k <= BW; k += blockDim.x) {
+        const int64_t row = j + k;
+        double v = 0.0;
+        if (row < m) {
+            if (row < r0) v = A[row * lda + j];
+            else if (have_r && row - r0 <= jj) v = R[(row - r0) * BW + jj];
+        }
+        Bd[j * (BW + 1) + k] = v;
+    }
+}
+
+// out = scale * in^T pieces / conversions ---------------------------------------------------
+__global__ void to_f64_kernel(const float *__restrict__ src, int64_t lds, int64_t rows, int64_t cols, double *__restrict__ dst, int64_t ldd)
+{
+    const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / cols, c = i - r * cols;
+        dst[r * ldd + c] = (double)__ldg(src + r * lds + c);
+    }
+}
+__global__ void to_f32_kernel(const double *__restrict__ src, int64_t lds, int64_t rows, int64_t cols, float *__restrict__ dst, int64_t ldd)
+{
+    const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / cols, c = i - r * cols;
+        dst[r * ldd + c] = (float)src[r * lds + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One CTA per shift: banded Cholesky of B + shift I in a sliding shared-memory window, fused with the forward
+// substitution of the right-hand sides; then the backward substitution from the stored factor.
+// rhs_t / sol_t are "vectors as rows": rhs_t[r][j] (shared by all shifts), sol_t[(g * nrhs + r)][j].
+// A column step is ~250 cycles of work but a global load is ~800 cycles away, so nothing on the critical path
+// waits for global memory: band columns / right-hand sides (forward) and factor columns (backward) arrive through
+// cp.async groups issued one chunk of 8 columns ahead.
+// ---------------------------------------------------------------------------------------------
+constexpr int WIN = BW + 1;             // columns a step touches: j .. j + BW
+constexpr int CH = 8;                   // prefetch chunk (columns)
+constexpr int SLOTS = WIN + 2 * CH;     // circular window: live columns + the chunk in flight + the chunk being consumed
+constexpr int RHS_MAX = 48;
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 1)
+band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const double *__restrict__ shifts, const double *__restrict__ rhs_t,
+                           int64_t ldr, int nrhs, double *__restrict__ Lg /*[G][m][WIN]*/, double *__restrict__ sol_t, int64_t lds,
+                           int *__restrict__ info)
+{
+    extern __shared__ double sm[];
+    double *win = sm;                                       // SLOTS x WIN: slot (j % SLOTS) holds column j: A[j + k][j], k = 0..BW
+    double *rwin = win + SLOTS * WIN;                       // SLOTS x RHS_MAX: right-hand-side rows / solution rows
+    double *lcol = rwin + SLOTS * RHS_MAX;                  // WIN: the finished column of L
+    double *ycur = lcol + WIN;                              // RHS_MAX
+    const int g = blockIdx.x, t = threadIdx.x;
+    const double shift = shifts[g];
+    double *L = Lg + (int64_t)g * m * WIN;
+    double *sol = sol_t + (int64_t)g * nrhs * lds;
+    int bad = 0;
+
+    auto prefetch_columns = [&](int64_t first, int count) {  // asynchronous: band columns + right-hand-side rows
+        for (int idx = t; idx < count * WIN; idx += blockDim.x) {
+            const int64_t j = first + idx / WIN;
+            const int k = idx % WIN;
+            if (j < m) cp_async8(&win[(int)(j % SLOTS) * WIN + k], Bd + j * WIN + k);
+        }
+        for (int idx = t; idx < count * nrhs; idx += blockDim.x) {
+            const int64_t j = first + idx / nrhs;
+            const int r = idx % nrhs;
+            if (j < m) cp_async8(&rwin[(int)(j % SLOTS) * RHS_MAX + r], rhs_t + (int64_t)r * ldr + j);
+        }
+        cp_async_commit();
+    };
+    prefetch_columns(0, WIN + CH);                          // columns 0 .. WIN + CH - 1
+    cp_async_wait_all();
+    __syncthreads();
+    prefetch_columns(WIN + CH, CH);                         // in flight while the first chunk is factorised
+
+    // ---- factorisation + forward substitution
+    for (int64_t j = 0; j < m; ++j) {
+        if (j > 0 && j % CH == 0) {
+            // columns up to j + WIN + CH - 1 are needed during this chunk: the group issued one chunk ago has them
+            cp_async_wait_all();
+            __syncthreads();
+            prefetch_columns(j + WIN + CH, CH);              // their slots held columns j - CH .. j - 1 (finished)
+        }
+        const int slot = (int)(j % SLOTS);
+        const int kn = (int)min((int64_t)BW, m - 1 - j);
+        const double d = win[slot * WIN] + shift;
+        const double ljj = sqrt(d);
+        if (!(d > 0.0)) bad = 1;
+        const double inv = 1.0 / ljj;
+        if (t <= kn) {
+            const double v = (t == 0) ? ljj : win[slot * WIN + t] * inv;
+            lcol[t] = v;
+            L[j * WIN + t] = v;
+        } else if (t < WIN) {
+            L[j * WIN + t] = 0.0;
+        }
+        if (t >= 128 && t - 128 < nrhs) {
+            const double y = rwin[slot * RHS_MAX + (t - 128)] * inv;
+            ycur[t - 128] = y;
+            sol[(int64_t)(t - 128) * lds + j] = y;            // y, overwritten by z in the backward pass
+        }
+        __syncthreads();
+        // trailing update of the window: A[j+i][j+l] -= L[i] L[l], 1 <= l <= i <= kn  (slot of column j+l, offset i-l)
+        for (int idx = t; idx < kn * kn; idx += blockDim.x) {
+            const int l = idx / kn + 1, i = idx % kn + 1;
+            if (i >= l) {
+                const int sl = (int)((j + l) % SLOTS);
+                win[sl * WIN + (i - l)] = fma(-lcol[i], lcol[l], win[sl * WIN + (i - l)]);
+            }
+        }
+        for (int idx = t; idx < kn * nrhs; idx += blockDim.x) {
+            const int i = idx / nrhs + 1, r = idx % nrhs;
+            const int sl = (int)((j + i) % SLOTS);
+            rwin[sl * RHS_MAX + r] = fma(-lcol[i], ycur[r], rwin[sl * RHS_MAX + r]);
+        }
+        __syncthreads();
+    }
+    cp_async_wait_all();
+    if (bad && t == 0) atomicAdd(info, 1);
+    __syncthreads();
+
+    // ---- backward substitution: z_j = (y_j - sum_{i=1..kn} L[j+i][j] z_{j+i}) / L[j][j]
+    // the factor columns and y rows of chunk c+1 are fetched (cp.async) while chunk c is processed
+    double *lring = win;                                    // 2 chunks x CH x WIN   (the window is free now)
+    double *yring = win + 2 * CH * WIN;                     // 2 chunks x CH x RHS_MAX
+    double *scratch = yring + 2 * CH * RHS_MAX;             // 256 partial sums
+    auto prefetch_back = [&](int64_t top, int buf) {        // columns top, top-1, ..., top-CH+1
+        for (int idx = t; idx < CH * WIN; idx += blockDim.x) {
+            const int64_t j = top - idx / WIN;
+            if (j >= 0) cp_async8(&lring[(buf * CH + idx / WIN) * WIN + idx % WIN], L + j * WIN + idx % WIN);
+        }
+        for (int idx = t; idx < CH * nrhs; idx += blockDim.x) {
+            const int64_t j = top - idx / nrhs;
+            if (j >= 0) cp_async8(&yring[(buf * CH + idx / nrhs) * RHS_MAX + idx % nrhs], sol + (int64_t)(idx % nrhs) * lds + j);
+        }
+        cp_async_commit();
+    };
+    __threadfence_block();
+    prefetch_back(m - 1, 0);
+    int buf = 0;
+    for (int64_t top = m - 1; top >= 0; top -= CH, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();
+        prefetch_back(top - CH, buf ^ 1);
+        for (int q = 0; q < CH; ++q) {
+            const int64_t j = top - q;
+            if (j < 0) break;
+            const int kn = (int)min((int64_t)BW, m - 1 - j);
+            const double *lc = lring + (buf * CH + q) * WIN;
+            const int r = t / 5, part = t % 5;               // 5 threads per right-hand side share the dot product
+            double sum = 0.0;
+            if (r < nrhs)
+                for (int i = 1 + part; i <= kn; i += 5) sum = fma(lc[i], rwin[(int)((j + i) % SLOTS) * RHS_MAX + r], sum);
+            scratch[t] = sum;
+            __syncthreads();
+            if (t < nrhs) {
+                const double tot = scratch[t * 5] + scratch[t * 5 + 1] + scratch[t * 5 + 2] + scratch[t * 5 + 3] + scratch[t * 5 + 4];
+                const double z = (yring[(buf * CH + q) * RHS_MAX + t] - tot) / lc[0];
+                rwin[(int)(j % SLOTS) * RHS_MAX + t] = z;
+                sol[(int64_t)t * lds + j] = z;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct Plan {
+    int64_t m, C, G, panels, lda;
+    size_t off_A, off_V, off_T, off_R, off_tau, off_Y, off_W, off_M1, off_M2, off_tmp, off_gbuf, off_rowk, off_counter, off_Bd,
+        off_rhs, off_P, off_L, off_sol, total;
+};
+
+static Plan make_plan(int64_t m, int64_t C, int64_t G)
+{
+    Plan p;
+    p.m = m; p.C = C; p.G = G;
+    p.panels = m > BW ? ceil_div(m, BW) - 1 : 0;
+    p.lda = round_up(m, 2);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    p.off_A = take((size_t)m * p.lda * 8);
+    // V of every panel (needed again for the two transforms of the right-hand sides): sum_p s_p x BW
+    size_t vrows = 0;
+    for (int64_t q = 0; q < p.panels; ++q) vrows += (size_t)(m - (q + 1) * BW);
+    p.off_V = take(vrows * BW * 8);
+    p.off_T = take((size_t)std::max<int64_t>(p.panels, 1) * BW * BW * 8);
+    p.off_R = take((size_t)BW * BW * 8);
+    p.off_tau = take((size_t)BW * 8);
+    p.off_Y = take((size_t)m * BW * 8);
+    p.off_W = take((size_t)m * BW * 8);
+    p.off_M1 = take((size_t)BW * BW * 8);
+    p.off_M2 = take((size_t)BW * BW * 8);
+    p.off_tmp = take((size_t)BW * BW * 8);
+    p.off_gbuf = take((size_t)3 * BW * 8);
+    p.off_rowk = take((size_t)3 * BW * 8);
+    p.off_counter = take(256);
+    p.off_Bd = take((size_t)m * (BW + 1) * 8);
+    p.off_rhs = take((size_t)C * m * 8);
+    p.off_P = take((size_t)G * C * BW * 8);
+    p.off_L = take((size_t)G * m * (BW + 1) * 8);
+    p.off_sol = take((size_t)G * C * m * 8);
+    p.total = off + 256;
+    return p;
+}
+
+// rows [r0, m) of the vectors-as-rows block X [n_vec x m] <- (I - V T' V^T) applied from the right:  X -= (X V) T' V^T
+// with T' = T for Q_p^T (transposed form of C -= V T^T V^T C) and T' = T^T for Q_p.
+static int apply_reflector(double *X, int64_t ldx, int64_t n_vec, int64_t r0, int64_t s, const double *V, const double *T,
+                           bool transpose_t, double *P, cudaStream_t st)
+{
+    int rc;
+    // P = X[:, r0:] V            (n_vec x BW, contraction over the s rows)
+    const int splits = splits_for(n_vec, BW, s);
+    if (splits > 1) GNNGP_CUDA(cudaMemsetAsync(P, 0, (size_t)n_vec * BW * 8, st));
+    if ((rc = dgemm(n_vec, BW, s, View{X + r0, ldx, 1}, View{V, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, P, BW, splits, st)) != GNNGP_OK) return rc;
+    // P2 = P T'  (stored behind P);  B(k, j) = T'[k][j]
+    double *P2 = P + n_vec * BW;
+    const View tv = transpose_t ? View{T, 1, BW} : View{T, BW, 1};
+    if ((rc = dgemm(n_vec, BW, BW, View{P, BW, 1}, tv, 0, kNoView, kNoView, 1.0, 0.0, P2, BW, 1, st)) != GNNGP_OK) return rc;
+    // X[:, r0:] -= P2 V^T        B(k, j) = V[j][k]
+    return dgemm(n_vec, s, BW, View{P2, BW, 1}, View{V, 1, BW}, 0, kNoView, kNoView, -1.0, 1.0, X + r0, ldx, 1, st);
+}
+
+}  // namespace bandfit
+}  // namespace gnngp
+
+using namespace gnngp;
+using namespace gnngp::bandfit;
+
+extern "C" size_t gnngp_band_fit_workspace_bytes(int64_t m, int64_t C, int64_t G)
+{
+    if (m <= 0 || C <= 0 || G <= 0) return 256;
+    Plan p = make_plan(m, C, G);
+    // apply_reflector keeps P and P2 back to back: 2 x (G*C) x BW
+    return p.total + (size_t)G * C * BW * 8;
+}
+
+extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, const float *rhs_t, int64_t ldr, int64_t C,
+                                  const double *shifts, int64_t G, float *coeff_t, int64_t ldo, int32_t *info, void *workspace,
+                                  size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(m > 0 && C > 0 && G > 0 && gram && rhs_t && shifts && coeff_t && info, "band_fit: bad arguments");
+    GNNGP_REQUIRE(ldg >= m && ldr >= m && ldo >= m, "band_fit: leading dimension too small");
+    GNNGP_REQUIRE(C <= RHS_MAX, "band_fit: at most %d right-hand sides per shift (got %lld)", RHS_MAX, (long long)C);
+    GNNGP_REQUIRE(workspace && aligned(workspace, 256) && workspace_bytes >= gnngp_band_fit_workspace_bytes(m, C, G),
+                  "band_fit: workspace must be 256-byte aligned and hold gnngp_band_fit_workspace_bytes(m, C, G)");
+    cudaStream_t st = as_stream(stream);
+    Plan p = make_plan(m, C, G);
+    char *base = reinterpret_cast<char *>(workspace);
+    double *A = reinterpret_cast<double *>(base + p.off_A);
+    double *Vall = reinterpret_cast<double *>(base + p.off_V);
+    double *Tall = reinterpret_cast<double *>(base + p.off_T);
+    double *R = reinterpret_cast<double *>(base + p.off_R);
+    double *tau = reinterpret_cast<double *>(base + p.off_tau);
+    double *Y = reinterpret_cast<double *>(base + p.off_Y);
+    double *W = reinterpret_cast<double *>(base + p.off_W);
+    double *M1 = reinterpret_cast<double *>(base + p.off_M1);
+    double *M2 = reinterpret_cast<double *>(base + p.off_M2);
+    double *tmp = reinterpret_cast<double *>(base + p.off_tmp);
+    double *gbuf = reinterpret_cast<double *>(base + p.off_gbuf);
+    double *rowk = reinterpret_cast<double *>(base + p.off_rowk);
+    unsigned int *counter = reinterpret_cast<unsigned int *>(base + p.off_counter);
+    double *Bd = reinterpret_cast<double *>(base + p.off_Bd);
+    double *rhs = reinterpret_cast<double *>(base + p.off_rhs);
+    double *P = reinterpret_cast<double *>(base + p.off_P);
+    double *Lg = reinterpret_cast<double *>(base + p.off_L);
+    double *sol = reinterpret_cast<double *>(base + p.off_sol);
+    const int64_t lda = p.lda;
+    const int sms = sm_count();
+    int rc;
+
+    GNNGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    symmetrize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(m * m, 256), (int64_t)sms * 16), 256, 0, st>>>(gram, ldg, m, A, lda);
+    GNNGP_LAUNCHED();
+    to_f64_kernel<<<(unsigned)std::min<int64_t>(ceil_div(C * m, 256), (int64_t)sms * 8), 256, 0, st>>>(rhs_t, ldr, C, m, rhs, m);
+    GNNGP_LAUNCHED();
+
+    // ---- band reduction, one panel at a time; the right-hand sides are transformed along the way (Q_p^T)
+    int coop = 0, dev = 0;
+    GNNGP_CUDA(cudaGetDevice(&dev));
+    GNNGP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GNNGP_REQUIRE(coop, "band_fit: the device does not support cooperative launches");
+    double *Vp = Vall;
+    for (int64_t q = 0; q < p.panels; ++q) {
+        const int64_t j0 = q * BW, r0 = j0 + BW, s = m - r0;
+        // rows per CTA: at least BW (row k of every step lives in CTA 0), at most what fits shared memory
+        int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, sms), 8));
+        GNNGP_REQUIRE(rows_per <= 208, "band_fit: m = %lld is too large for the shared-memory panel (max ~30 000)", (long long)m);
+        const int n_cta = (int)ceil_div(s, rows_per);
+        const size_t smem = (size_t)rows_per * LDP * sizeof(double);
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_kernel), 208 * LDP * (int)sizeof(double)));
+        GNNGP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+        const double *Ap = A + r0 * lda + j0;
+        double *Tq = Tall + q * BW * BW;
+        int rows_arg = rows_per;
+        int64_t lda_arg = lda, s_arg = s;
+        void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&tau,
+                        (void *)&gbuf, (void *)&rowk, (void *)&counter};
+        GNNGP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(sbr_panel_kernel), dim3(n_cta), dim3(256), args, smem, st));
+        count_launch();
+        band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
+        GNNGP_LAUNCHED();
+        // T from V^T V and tau
+        {
+            const int sp = splits_for(BW, BW, s);
+            if (sp > 1) GNNGP_CUDA(cudaMemsetAsync(tmp, 0, (size_t)BW * BW * 8, st));
+            if ((rc = dgemm(BW, BW, s, View{Vp, 1, BW}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, tmp, BW, sp, st)) != GNNGP_OK) return rc;
+            GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(larft_kernel), BW * LDP * (int)sizeof(double)));
+            larft_kernel<<<1, BW, (size_t)BW * LDP * sizeof(double), st>>>(tmp, tau, Tq);
+            GNNGP_LAUNCHED();
+        }
+        double *A22 = A + r0 * lda + r0;
+        // Y = A22 V
+        if ((rc = dgemm(s, BW, s, View{A22, lda, 1}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, Y, BW, 1, st)) != GNNGP_OK) return rc;
+        // M1 = V^T Y
+        {
+            const int sp = splits_for(BW, BW, s);
+            if (sp > 1) GNNGP_CUDA(cudaMemsetAsync(M1, 0, (size_t)BW * BW * 8, st));
+            if ((rc = dgemm(BW, BW, s, View{Vp, 1, BW}, View{Y, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, M1, BW, sp, st)) != GNNGP_OK) return rc;
+        }
+        // M2 = -1/2 T^T M1 T
+        if ((rc = dgemm(BW, BW, BW, View{M1, BW, 1}, View{Tq, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, tmp, BW, 1, st)) != GNNGP_OK) return rc;
+        if ((rc = dgemm(BW, BW, BW, View{Tq, 1, BW}, View{tmp, BW, 1}, 0, kNoView, kNoView, -0.5, 0.0, M2, BW, 1, st)) != GNNGP_OK) return rc;
+        // W = Y T + V M2
+        if ((rc = dgemm(s, BW, BW, View{Y, BW, 1}, View{Tq, BW, 1}, BW, View{Vp, BW, 1}, View{M2, BW, 1}, 1.0, 0.0, W, BW, 1, st)) != GNNGP_OK) return rc;
+        // A22 -= V W^T + W V^T        B(k, j) = W[j][k] / V[j][k]
+        if ((rc = dgemm(s, s, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st)) != GNNGP_OK) return rc;
+        // right-hand sides: rhs[:, r0:] <- rhs[:, r0:] (I - V T V^T)   (= (Q_p^T c)^T)
+        if ((rc = apply_reflector(rhs, m, C, r0, s, Vp, Tq, false, P, st)) != GNNGP_OK) return rc;
+        Vp += s * BW;
+    }
+    // last block: already inside the band
+    for (int64_t j0 = p.panels * BW; j0 < m; j0 += BW) {
+        band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 0, Bd);
+        GNNGP_LAUNCHED();
+    }
+
+    // ---- one CTA per shift: banded Cholesky + substitutions
+    {
+        const size_t smem = (size_t)(SLOTS * WIN + SLOTS * RHS_MAX + WIN + RHS_MAX) * sizeof(double);
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(band_cholesky_solve_kernel), (int)smem));
+        band_cholesky_solve_kernel<<<(unsigned)G, 256, smem, st>>>(Bd, m, shifts, rhs, m, (int)C, Lg, sol, m, info);
+        GNNGP_LAUNCHED();
+    }
+    // ---- solutions back to the original basis: sol <- sol Q_p^T for p = last .. 0   (x = Q_0 Q_1 ... z)
+    Vp = Vall;
+    std::vector<double *> vptr(p.panels);
+    for (int64_t q = 0; q < p.panels; ++q) { vptr[q] = Vp; Vp += (m - (q + 1) * BW) * BW; }
+    for (int64_t q = p.panels - 1; q >= 0; --q) {
+        const int64_t r0 = (q + 1) * BW, s = m - r0;
+        if ((rc = apply_reflector(sol, m, G * C, r0, s, vptr[q], Tall + q * BW * BW, true, P, st)) != GNNGP_OK) return rc;
+    }
+    to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(G * C * m, 256), (int64_t)sms * 16), 256, 0, st>>>(sol, m, G * C, m, coeff_t, ldo);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}

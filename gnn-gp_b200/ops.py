@@ -541,6 +541,28 @@ class CudaOps(object):
         self._check(rhs_t, "rhs_t", dims=2)
         return _shifted_solves(self, gram, rhs_t, shifts)
 
+    def band_fit(self, gram: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.Tensor):
+        """``(gram + shifts[g] I)⁻¹ rhs`` for every shift WITHOUT an eigendecomposition (``csrc/bandfit.cu``): fp64 band
+        reduction of the Gram matrix with block reflectors in GEMM form, then one banded Cholesky and two substitutions
+        per shift.  ``gram`` fp32 [m x m] with a valid LOWER triangle (``syrk``'s output), ``rhs_t`` fp32 [C x m],
+        ``shifts`` fp64 [G] on the device.  Returns (coefficients fp32 [(G*C) x m] — the B operand of ``nugget_sweep`` —
+        and a device int32 counting shifts whose factorisation met a non-positive pivot).  No host sync."""
+        gram, ldg = self._mat(gram, "gram")
+        rhs_t, ldr = self._mat(rhs_t, "rhs_t")
+        self._check(shifts, "shifts", dtype=torch.float64, dims=1)
+        shifts = shifts.contiguous()
+        m, c, g = gram.shape[0], rhs_t.shape[0], shifts.numel()
+        if gram.shape[1] != m or rhs_t.shape[1] != m:
+            raise RuntimeError("band_fit: gram must be [m x m] and rhs_t [C x m]")
+        out = self.empty(g * c, m, gram.device)
+        info = torch.zeros(1, dtype=torch.int32, device=gram.device)
+        need = self.lib.query("gnngp_band_fit_workspace_bytes", m, c, g)
+        ws = self.workspace(need + 256, gram.device, "bandfit")
+        wptr = (ws.data_ptr() + 255) // 256 * 256
+        self.lib.call("gnngp_band_fit_f64", gram.data_ptr(), ldg, m, rhs_t.data_ptr(), ldr, c, shifts.data_ptr(), g,
+                      out.data_ptr(), self._ld(out), info.data_ptr(), wptr, need, self._stream())
+        return out, info
+
     def potrs_batched(self, factors: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
         """``X_b = (L_b L_bᵀ)⁻¹ rhs`` for a stack of fp64 lower Cholesky factors [b, m, m] and one fp64
         right-hand-side block [m, c], in one launch of ``potrs_batched_kernel``.  Returns fp64 [b, m, c]."""

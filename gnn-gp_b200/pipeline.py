@@ -496,17 +496,40 @@ class Pipeline(object):
             comm.all_reduce_sum(gram)
             comm.all_reduce_sum(qty_t)
             comm.all_reduce_sum(scale)
-        if self._fit_solver(gram.shape[0], nugget.numel()) == "cholesky":
+        solver = self._fit_solver(gram.shape[0], nugget.numel(), qty_t.shape[0])
+        if solver == "cholesky":
             fitted = self._fit_by_shifted_solves(q, gram, qty_t, scale, nugget, trailing)
             if fitted is not None:
                 self.last_fit_solver = "cholesky"
+                return fitted
+        elif solver == "band":
+            fitted = self._fit_by_band_reduction(q, gram, qty_t, scale, nugget, trailing)
+            if fitted is not None:
+                self.last_fit_solver = "band"
                 return fitted
         self.last_fit_solver = "eigh"
         evals, evecs = ops.eigh(gram)
         proj_t = ops.gemm_nt(qty_t, ops.transpose(evecs))             # (V^T Q_b^T y_b)^T  [C x m]
         return self._sweep(q, evals, evecs, proj_t, scale, nugget, trailing)
 
-    def _fit_solver(self, m: int, n_nuggets: int) -> str:
+    def _fit_by_band_reduction(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
+                               nugget: torch.Tensor, trailing):
+        """All nuggets' coefficient blocks ``(Q_bᵀQ_b + eps d I)⁻¹ Q_bᵀy_b`` from ONE fp64 band reduction of the Gram
+        matrix and a banded Cholesky per nugget (``ops.band_fit``, csrc/bandfit.cu) — no eigendecomposition.
+        ``V diag(1/(w + eps d)) Vᵀ`` of src/predict.py:57-62 IS that inverse; the result feeds the same single sweep
+        contraction.  Returns None when a shifted matrix is not numerically positive definite (the Gram is fp32: its
+        rounding noise can exceed the smallest shift); the caller then takes the eigen route, like the reference."""
+        ops = self.ops
+        g, c = nugget.numel(), qty_t.shape[0]
+        shifts = (nugget.to(torch.float64) * scale.to(torch.float64)).contiguous()
+        coeff_t, info = ops.band_fit(gram, qty_t, shifts)
+        if int(info.item()) > 0:                                      # one small device->host read (the eigen route syncs too)
+            return None
+        fitted = ops.nugget_sweep(q, coeff_t, g, c)
+        fitted = fitted.reshape((g, q.shape[0]) + tuple(trailing))
+        return fitted[0] if g == 1 else fitted
+
+    def _fit_solver(self, m: int, n_nuggets: int, n_targets: int = 1) -> str:
         """``eigh`` (the reference's algorithm, src/predict.py:57-62: one m x m eigendecomposition serves all
         nuggets) or ``cholesky`` (nugget-parallel: every rank factorises ``Q_bᵀQ_b + eps d I`` for ITS share of
         the nugget grid).  The eigendecomposition cannot be sharded and is replicated on every rank — the
@@ -521,8 +544,15 @@ class Pipeline(object):
         mode = os.environ.get("GNNGP_FIT_SOLVER", "auto")
         if mode in ("eigh", "cholesky"):
             return mode
+        band_ok = hasattr(self.ops, "band_fit") and n_targets <= 48 and m <= 29000
+        if mode == "band":
+            return "band" if band_ok else "eigh"
         world = self.comm.world
-        if world < 2 or m < 2048:
+        if world < 2:
+            # single GPU: the band reduction (BLAS-3, own kernels) replaces the m x m eigendecomposition from the size
+            # where cuSOLVER's one-stage tridiagonalisation dominates the step
+            return "band" if band_ok and m >= 1024 else "eigh"
+        if m < 2048:
             return "eigh"
         per_rank = (n_nuggets + world - 1) // world
         return "cholesky" if per_rank < 30.0 * (m / 3025.0) ** 0.3 else "eigh"

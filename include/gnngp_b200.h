@@ -194,6 +194,19 @@ int gnngp_argmax_count(const float *fitted, const int64_t *y, const uint8_t *mem
 int gnngp_sqerr_sum(const float *fitted, const float *y, const uint8_t *membership, int64_t G, int64_t n,
                     int64_t k, double *sse, gnngp_stream_t stream);
 
+/* ---- K9: posterior solve for all nuggets by band reduction (csrc/bandfit.cu) ------------------------------------
+ * Replaces `w, v = torch.linalg.eigh(Q[mb].T @ Q[mb])` and the per-nugget `v @ (temp / (w + eps*d))` of
+ * src/predict.py:57-62.  gram: fp32 [m x m], LOWER triangle valid (gnngp_syrk_f32's output); rhs_t: fp32 [C x m] =
+ * (Q_b^T y_b)^T; shifts: fp64 [G] on the device (eps_g * d); coeff_t: fp32 [(G*C) x m], row g*C + c =
+ * ((gram + shifts[g] I)^-1 rhs)[:, c] — the B^T operand of gnngp_nugget_sweep_f32.  info (device int32): number of
+ * shifts whose banded Cholesky met a non-positive pivot (the caller then takes the eigen route).  fp64 throughout:
+ * successive band reduction to bandwidth 128 with block reflectors in GEMM form, one banded Cholesky + two
+ * substitutions per shift.  C <= 48.  No host synchronisation. */
+size_t gnngp_band_fit_workspace_bytes(int64_t m, int64_t C, int64_t G);
+int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, const float *rhs_t, int64_t ldr, int64_t C,
+                       const double *shifts, int64_t G, float *coeff_t, int64_t ldo, int32_t *info, void *workspace,
+                       size_t workspace_bytes, gnngp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,6 +143,11 @@ class StubOps(object):
             out[i * c:(i + 1) * c] = torch.cholesky_solve(rhs_t.double().T.contiguous(), factor).T.float()
         return out, bad
 
+    def band_fit(self, gram, rhs_t, shifts):
+        """Stand-in of csrc/bandfit.cu: the same shifted solves through dense fp64 Cholesky factorisations."""
+        out, bad = self.shifted_solves(gram, rhs_t, shifts)
+        return out, bad.to(torch.int32).reshape(1)
+
     def nystrom_spectrum(self, D):
         root = torch.sqrt(torch.clamp(D, 0))
         return root, root / torch.clamp(D, D[-1] * 1e-4)

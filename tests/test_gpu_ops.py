@@ -319,3 +319,40 @@ def test_shifted_solves_match_stub(ops, ref):
     _, bad = ops.shifted_solves(torch.diag(torch.tensor([1.0, -2.0, 3.0])).cuda(), torch.ones(2, 3).cuda(),
                                 torch.tensor([0.5], dtype=torch.float64).cuda())
     assert int(bad) == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K9: the eigen-free posterior solve (csrc/bandfit.cu)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,c,g,rank", [(700, 5, 7, 300), (129, 3, 4, 129), (1, 2, 3, 1), (128, 4, 2, 60), (1500, 41, 11, 400),
+                                        (257, 48, 3, 257), (3053, 41, 101, 700)])
+def test_band_fit_matches_dense_fp64_solves(ops, m, c, g, rank):
+    """(G + shift I)^-1 rhs for every shift against torch's fp64 dense solve, on PSD Gram matrices that are
+    rank-deficient like Q_b^T Q_b (most eigenvalues far below the shifts), ragged sizes around the band width."""
+    gen = torch.Generator(device="cuda").manual_seed(m + c)
+    x = torch.randn(m, rank, device="cuda", generator=gen, dtype=torch.float64)
+    x = x * torch.logspace(0, -4, rank, device="cuda", dtype=torch.float64)
+    gram64 = x @ x.T
+    gram = torch.tril(gram64).float()                               # only the lower triangle is meaningful
+    gram = gram + torch.triu(torch.full_like(gram, 7.0), 1)         # garbage above the diagonal must be ignored
+    rhs_t = torch.randn(c, m, device="cuda", generator=gen)
+    scale = float(gram64.diagonal().mean())
+    shifts = torch.logspace(-3, 1, g, device="cuda", dtype=torch.float64) * scale
+    got, info = ops.band_fit(gram, rhs_t, shifts)
+    torch.cuda.synchronize()
+    assert int(info) == 0
+    sym = torch.tril(gram).double()
+    sym = sym + torch.tril(sym, -1).T
+    eye = torch.eye(m, device="cuda", dtype=torch.float64)
+    for i in range(g):
+        want = torch.linalg.solve(sym + shifts[i] * eye, rhs_t.double().T).T          # [c x m]
+        block = got[i * c:(i + 1) * c].double()
+        err = float((block - want).norm() / want.norm())
+        assert err < 5e-7, (m, i, err)                                                 # fp32 output rounding only
+
+
+def test_band_fit_reports_an_indefinite_shifted_matrix(ops):
+    gram = torch.diag(torch.tensor([4.0, 1.0, -0.5, 2.0] * 50, device="cuda"))
+    rhs_t = torch.ones(2, 200, device="cuda")
+    _, info = ops.band_fit(gram, rhs_t, torch.tensor([0.1, 1.0], device="cuda", dtype=torch.float64))
+    assert int(info) == 1                                             # the shift 0.1 leaves -0.4 on the diagonal

@@ -77,6 +77,18 @@ def test_nugget_parallel_fit_matches_reference_golden(name, monkeypatch):
     runner.check_against_golden(name, out, masks)
 
 
+@pytest.mark.parametrize("name", ["small-GCN-nys4-L2", "tinyreg-GIN-nys1-L3", "pubmed-GCN-nys4-L2", "chameleon-SAGE-nys1-L2",
+                                  "tiny-GCN-nys8-L2"])
+def test_band_reduction_fit_matches_reference_golden(name, monkeypatch):
+    """The eigen-free fit route (fp64 band reduction + banded Cholesky per nugget, csrc/bandfit.cu) forced on every
+    size: same golden check as the eigen route — posterior means, argmax, accuracy / R² curves."""
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "band")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    out, model = run_public_api(case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+
+
 def test_reuse_products_across_a_sweep_matches_fresh_models():
     """SURVEY §8f N4 through the public API: with ``reuse_products`` a sigma_w / L sweep keeps A @ Q0 and
     gives the same kernels and metrics as a fresh model per setting."""

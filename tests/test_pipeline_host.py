@@ -51,6 +51,17 @@ def test_nugget_parallel_cholesky_fit_matches_reference(name, monkeypatch):
     runner.check_against_golden(name, out, masks)
 
 
+@pytest.mark.parametrize("name", ["tiny-GCN-nys2-L3", "tinyreg-GIN-nys1-L3", "small-SAGE-nys4-L4"])
+def test_band_reduction_fit_route_matches_reference(name, monkeypatch):
+    """The single-GPU fit route without an eigendecomposition (pipeline._fit_by_band_reduction; the CUDA operator is
+    csrc/bandfit.cu, here its dense stand-in) gives the reference's posterior means: golden check."""
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "band")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    out = runner.run_pipeline(StubOps(), case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+
+
 def test_fit_solver_policy(monkeypatch):
     from gnngp_b200.pipeline import Pipeline
 
@@ -61,7 +72,11 @@ def test_fit_solver_policy(monkeypatch):
             self.world = world
 
     monkeypatch.delenv("GNNGP_FIT_SOLVER", raising=False)
-    assert Pipeline(StubOps(), Comm(1))._fit_solver(15356, 101) == "eigh"        # one rank: one eigh beats 101 solves
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(15356, 101, 41) == "band"    # one rank: band reduction replaces the eigh
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(3053, 101, 41) == "band"
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(600, 101, 41) == "eigh"      # small block: eigh is cheap
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(15356, 101, 100) == "eigh"   # more targets than the solve kernel holds
+    assert Pipeline(StubOps(), Comm(1))._fit_solver(31000, 101, 41) == "eigh"    # beyond the shared-memory panel
     assert Pipeline(StubOps(), Comm(2))._fit_solver(3025, 101) == "eigh"         # 51 solves per rank cost more than one eigh
     assert Pipeline(StubOps(), Comm(2))._fit_solver(15356, 101) == "eigh"
     assert Pipeline(StubOps(), Comm(4))._fit_solver(3025, 101) == "cholesky"     # 26 x 1.7 ms < 52 ms
