@@ -32,23 +32,34 @@ constexpr int BW = 128;                 // bandwidth of the reduced matrix = pan
 constexpr int LDP = BW + 1;             // padded slab row (bank-conflict-free column walks)
 
 // ---------------------------------------------------------------------------------------------
-// generic fp64 GEMM on CUDA cores:  C = alpha * (A1 B1 + A2 B2) + beta * C   (or atomic accumulation for split-K)
-// operands are strided views: A(i, k) = p[i * rs + k * cs], B(k, j) = p[k * rs + j * cs]; one of the two strides
-// of every operand is 1.  128 x 64 tiles, K steps of 16, 8 x 4 accumulators per thread, register prefetch.
+// generic fp64 GEMM on the fp64 tensor path (mma.sync m8n8k4):  C = alpha * (A1 B1 + A2 B2) + beta * C   (or atomic
+// accumulation for split-K).  Operands are strided views: A(i, k) = p[i * rs + k * cs], B(k, j) = p[k * rs + j * cs];
+// one of the two strides of every operand is 1.  CTA tile 128 x 64, K steps of 16, 8 warps of 32 x 32 (4 x 4 DMMA
+// fragments each: 16 FMA per double read from shared memory — the CUDA-core version with an 8 x 4 register tile read
+// 96 B per 32 FMA and was shared-memory-bound at 13.6 TFLOP/s).  Both operand tiles sit in shared memory as
+// [row][k] with a row pitch of 20 doubles: the fragment loads of a half-warp (4 rows x 4 k) hit 16 distinct banks.
 // ---------------------------------------------------------------------------------------------
 struct View { const double *p; int64_t rs, cs; };
 
-constexpr int GM = 128, GN = 64, GK = 16;
+constexpr int GM = 128, GN = 64, GK = 16, GLD = GK + 4;
+
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
 
 template <bool ATOMIC>
 __global__ void __launch_bounds__(256, 2)
 dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1, View B1, View A2, View B2, double beta,
              double *__restrict__ C, int64_t ldc, int splits)
 {
-    __shared__ __align__(16) double As[GK][GM + 2];
-    __shared__ __align__(16) double Bs[GK][GN + 2];
+    __shared__ __align__(16) double As[GM][GLD];
+    __shared__ __align__(16) double Bs[GN][GLD];
     const int t = threadIdx.x;
-    const int tx = t & 15, ty = t >> 4;                     // 16 x 16 threads: 4 columns x 8 rows each
+    const int lane = t & 31, warp = t >> 5;
+    const int g = lane >> 2, t4 = lane & 3;                 // fragment coordinates
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;  // 4 x 2 warps
     const int64_t m0 = (int64_t)blockIdx.y * GM, n0 = (int64_t)blockIdx.x * GN;
     const int64_t tiles1 = (K1 + GK - 1) / GK, tiles2 = (K2 + GK - 1) / GK;
     const int64_t tiles = tiles1 + tiles2;
@@ -56,11 +67,11 @@ dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1
     const int64_t t_begin = (int64_t)blockIdx.z * per, t_end = min(tiles, t_begin + per);
     if (t_begin >= t_end) return;
 
-    double acc[8][4];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     double ra[8], rb[4];
     auto fetch = [&](int64_t kt) {
@@ -104,17 +115,17 @@ dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1
         const View A = second ? A2 : A1, B = second ? B2 : B1;
         if (A.cs == 1) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) As[t & 15][(t >> 4) + 16 * r] = ra[r];
+            for (int r = 0; r < 8; ++r) As[(t >> 4) + 16 * r][t & 15] = ra[r];
         } else {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) As[(t >> 7) + 2 * r][t & 127] = ra[r];
+            for (int r = 0; r < 8; ++r) As[t & 127][(t >> 7) + 2 * r] = ra[r];
         }
         if (B.cs == 1) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) Bs[(t >> 6) + 4 * r][t & 63] = rb[r];
+            for (int r = 0; r < 4; ++r) Bs[t & 63][(t >> 6) + 4 * r] = rb[r];
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) Bs[t & 15][(t >> 4) + 16 * r] = rb[r];
+            for (int r = 0; r < 4; ++r) Bs[(t >> 4) + 16 * r][t & 15] = rb[r];
         }
     };
 
@@ -125,35 +136,32 @@ dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1
         __syncthreads();
         if (kt + 1 < t_end) fetch(kt + 1);
 #pragma unroll
-        for (int kk = 0; kk < GK; ++kk) {
-            double a[8], b[4];
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const double2 v = *reinterpret_cast<const double2 *>(&As[kk][ty * 8 + i]);
-                a[i] = v.x; a[i + 1] = v.y;
-            }
+            for (int i = 0; i < 4; ++i) a[i] = As[wm + i * 8 + g][k4 + t4];
 #pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                const double2 v = *reinterpret_cast<const double2 *>(&Bs[kk][tx * 4 + j]);
-                b[j] = v.x; b[j + 1] = v.y;
-            }
+            for (int j = 0; j < 4; ++j) b[j] = Bs[wn + j * 8 + g][k4 + t4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t row = m0 + ty * 8 + i;
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = m0 + wm + i * 8 + g;
         if (row >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int64_t col = n0 + tx * 4 + j;
-            if (col >= N) continue;
-            double *c = C + row * ldc + col;
-            if (ATOMIC) atomicAdd(c, alpha * acc[i][j]);
-            else *c = (beta == 0.0) ? alpha * acc[i][j] : fma(beta, *c, alpha * acc[i][j]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t col = n0 + wn + j * 8 + t4 * 2 + e;
+                if (col >= N) continue;
+                double *c = C + row * ldc + col;
+                if (ATOMIC) atomicAdd(c, alpha * acc[i][j][e]);
+                else *c = (beta == 0.0) ? alpha * acc[i][j][e] : fma(beta, *c, alpha * acc[i][j][e]);
+            }
         }
     }
 }
@@ -221,31 +229,38 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 // ---------------------------------------------------------------------------------------------
 // Householder QR of one s x BW panel (the block below the band), cooperative grid.
 //
-// CTA c keeps rows [c * rows_per, ...) of the panel in shared memory for the whole factorisation.  Column step k:
+// CTA c < n_slab keeps rows [c * rows_per, ...) of the panel in shared memory for the whole factorisation.  Column step k:
 //   pass 1   every CTA adds its part of  g[c] = sum_{i >= k} P[i][c] * P[i][k]  (ALL columns c at once) to a global
 //            vector; CTA 0 (which owns the top BW rows, hence row k) also publishes row k.          -> ONE barrier
 //   pass 2   g[k] = |x|^2 gives the reflector (alpha, v0, tau); w = P^T v follows from g and row k WITHOUT a second
 //            reduction because v = (x - alpha e_1) / v0 differs from x in one entry: w[c] = (g[c] - alpha P[k][c]) / v0.
 //            Each CTA applies  P[i][c] -= tau v_i w[c]  (c > k) to its rows and overwrites column k with v.
-// The reduction vectors are triple-buffered: buffer (k+1) % 3 is cleared in step k, two barriers after its last read.
-// Output: V (explicit unit lower trapezoidal, s x BW, row-major), R (BW x BW upper triangle), tau (BW).
+// The same vector holds, for c < k, z[c] = V[:, c]^T v_k — exactly what the compact-WY factor needs:
+// T[:k, k] = -tau_k T[:k, :k] z (LAPACK dlarft).  The LAST CTA of the grid owns no rows: it keeps T in its shared
+// memory and computes one column per step while the others update their slabs, so T costs no time and no extra
+// launches.  The reduction vectors are triple-buffered: buffer (k+1) % 3 is cleared in step k, two barriers after its
+// last read.  Output: V (explicit unit lower trapezoidal, s x BW, row-major), R (BW x BW upper triangle), T (BW x BW).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
 sbr_panel_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows_per, double *__restrict__ V, double *__restrict__ R,
-                 double *__restrict__ tau_out, double *__restrict__ gbuf /*3 x BW*/, double *__restrict__ rowk /*3 x BW*/,
+                 double *__restrict__ T, double *__restrict__ gbuf /*3 x BW*/, double *__restrict__ rowk /*3 x BW*/,
                  unsigned int *counter)
 {
-    extern __shared__ double slab[];                        // rows_per x LDP
+    extern __shared__ double slab[];                        // rows_per x LDP (slab CTAs) / BW x LDP (the T CTA)
     __shared__ double w_s[BW];
     __shared__ double red[2][BW];
-    __shared__ double hh[4];                                // alpha, v0, tau, live flag
     const int t = threadIdx.x;
     const int c = t & (BW - 1), h = t >> 7;                 // column, half (two halves split the slab's rows)
+    const bool t_cta = blockIdx.x == gridDim.x - 1;         // the CTA that builds T
     const int64_t row0 = (int64_t)blockIdx.x * rows_per;
-    const int nrows = (int)max((int64_t)0, min((int64_t)rows_per, s - row0));
+    const int nrows = t_cta ? 0 : (int)max((int64_t)0, min((int64_t)rows_per, s - row0));
     unsigned int target = 0;
 
-    for (int i = h; i < nrows; i += 2) slab[i * LDP + c] = Ap[(row0 + i) * lda + c];
+    if (t_cta) {
+        for (int i = h; i < BW; i += 2) slab[i * LDP + c] = 0.0;
+    } else {
+        for (int i = h; i < nrows; i += 2) slab[i * LDP + c] = Ap[(row0 + i) * lda + c];
+    }
     if (blockIdx.x == 0)
         for (int i = t; i < 3 * BW; i += blockDim.x) gbuf[i] = 0.0;   // all three reduction buffers start clean
     const int steps = (int)min((int64_t)BW, s);
@@ -255,15 +270,19 @@ sbr_panel_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows
         double *g = gbuf + (k % 3) * BW;
         double *rk = rowk + (k % 3) * BW;
         // ---- pass 1: partial dots of column k (rows >= k) with every column
-        {
+        if (!t_cta) {
             const int lo = (int)max((int64_t)0, (int64_t)k - row0);       // first local row with global index >= k
-            double part = 0.0;
-            for (int i = lo + h; i < nrows; i += 2) part = fma(slab[i * LDP + c], slab[i * LDP + k], part);
-            red[h][c] = part;
+            double p0 = 0.0, p1 = 0.0;                                    // two chains: fp64 FMA latency
+            int i = lo + h;
+            for (; i + 2 < nrows; i += 4) {
+                p0 = fma(slab[i * LDP + c], slab[i * LDP + k], p0);
+                p1 = fma(slab[(i + 2) * LDP + c], slab[(i + 2) * LDP + k], p1);
+            }
+            for (; i < nrows; i += 2) p0 = fma(slab[i * LDP + c], slab[i * LDP + k], p0);
+            red[h][c] = p0 + p1;
             __syncthreads();
             if (h == 0) {
-                const double sum = red[0][c] + red[1][c];
-                if (nrows > lo) atomicAdd(g + c, sum);
+                if (nrows > lo) atomicAdd(g + c, red[0][c] + red[1][c]);
                 if (blockIdx.x == 0) {
                     rk[c] = slab[k * LDP + c];                             // row k lives in CTA 0 (k < BW <= rows_per)
                     gbuf[((k + 1) % 3) * BW + c] = 0.0;
@@ -271,42 +290,54 @@ sbr_panel_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows
             }
         }
         grid_barrier(counter, gridDim.x, target);
-        // ---- pass 2: reflector + rank-1 update of this CTA's rows
-        if (t == 0) {
-            const double nrm2 = __ldcg(g + k), x0 = __ldcg(rk + k);
-            if (!(nrm2 > 0.0)) { hh[0] = x0; hh[1] = 1.0; hh[2] = 0.0; hh[3] = 0.0; }     // zero column: H = I
-            else {
-                const double nrm = sqrt(nrm2);
-                const double alpha = x0 >= 0.0 ? -nrm : nrm;
-                hh[0] = alpha; hh[1] = x0 - alpha; hh[2] = (alpha - x0) / alpha; hh[3] = 1.0;
-            }
-        }
-        __syncthreads();
-        const double alpha = hh[0], v0 = hh[1], tau = hh[2];
-        const bool live = hh[3] != 0.0;
-        if (h == 0) w_s[c] = live ? (__ldcg(g + c) - alpha * __ldcg(rk + c)) / v0 : 0.0;
-        __syncthreads();
+        // ---- pass 2: every thread derives the reflector from g[k], row k (two broadcast loads + its own column)
+        const double nrm2 = __ldcg(g + k), x0 = __ldcg(rk + k);
+        const double gc = __ldcg(g + c), rc = __ldcg(rk + c);
+        const bool live = nrm2 > 0.0;                                      // zero column: H = I
+        double alpha = x0, inv_v0 = 1.0, tau = 0.0;
         if (live) {
-            const double wc = w_s[c];
+            const double nrm = sqrt(nrm2);
+            alpha = x0 >= 0.0 ? -nrm : nrm;
+            inv_v0 = 1.0 / (x0 - alpha);
+            tau = (alpha - x0) / alpha;
+        }
+        const double wc = live ? (gc - alpha * rc) * inv_v0 : 0.0;        // w[c] (c > k) and z[c] (c < k)
+        if (t_cta) {
+            // T[:k, k] = -tau T[:k, :k] z ;  T[k][k] = tau      (rows split over the 256 threads: r = c, halves share the dot)
+            if (h == 0) w_s[c] = (c < k) ? wc : 0.0;
+            __syncthreads();
+            if (c < k) {
+                double sum = 0.0;
+                for (int j = c + h; j < k; j += 2) sum = fma(slab[c * LDP + j], w_s[j], sum);   // upper triangular rows
+                red[h][c] = sum;
+            }
+            __syncthreads();
+            if (h == 0) {
+                if (c < k) slab[c * LDP + k] = -tau * (red[0][c] + red[1][c]);
+                else if (c == k) slab[c * LDP + k] = tau;
+            }
+            __syncthreads();
+            continue;
+        }
+        if (live) {
             const int lo = (int)max((int64_t)0, (int64_t)k + 1 - row0);   // rows strictly below row k
             if (c > k) {
-                for (int i = lo + h; i < nrows; i += 2) {
-                    const double vi = slab[i * LDP + k] / v0;
-                    slab[i * LDP + c] = fma(-tau * vi, wc, slab[i * LDP + c]);
-                }
+                const double f = -tau * inv_v0 * wc;
+                for (int i = lo + h; i < nrows; i += 2) slab[i * LDP + c] = fma(slab[i * LDP + k], f, slab[i * LDP + c]);
                 if (blockIdx.x == 0 && h == 0) slab[k * LDP + c] = fma(-tau, wc, slab[k * LDP + c]);   // row k: v_k = 1
             }
             __syncthreads();
             if (c == k) {
-                for (int i = lo + h; i < nrows; i += 2) slab[i * LDP + k] /= v0;
+                for (int i = lo + h; i < nrows; i += 2) slab[i * LDP + k] *= inv_v0;
                 if (blockIdx.x == 0 && h == 0) slab[k * LDP + k] = alpha;
             }
         }
-        if (blockIdx.x == 0 && t == 0) tau_out[k] = tau;
         __syncthreads();
     }
-    if (blockIdx.x == 0)
-        for (int k = steps + t; k < BW; k += blockDim.x) tau_out[k] = 0.0;
+    if (t_cta) {
+        for (int i = h; i < BW; i += 2) T[i * BW + c] = slab[i * LDP + c];
+        return;
+    }
     // ---- write V (explicit) and R
     for (int i = h; i < nrows; i += 2) {
         const int64_t gi = row0 + i;
@@ -319,31 +350,6 @@ sbr_panel_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows
     }
     if (blockIdx.x == 0)
         for (int64_t gi = s + h; gi < BW; gi += 2) R[gi * BW + c] = 0.0;     // panels shorter than BW rows
-}
-
-// T of the compact WY form from V^T V and tau (LAPACK dlarft, forward columnwise):  T[:k, k] = -tau_k T[:k, :k] (V^T V)[:k, k]
-__global__ void __launch_bounds__(BW, 1)
-larft_kernel(const double *__restrict__ VtV, const double *__restrict__ tau, double *__restrict__ T)
-{
-    extern __shared__ double Ts[];                          // BW x LDP
-    __shared__ double z[BW];
-    const int r = threadIdx.x;
-    for (int cidx = 0; cidx < BW; ++cidx) Ts[r * LDP + cidx] = 0.0;
-    __syncthreads();
-    for (int k = 0; k < BW; ++k) {
-        const double tk = tau[k];
-        z[r] = (r < k) ? VtV[r * BW + k] : 0.0;
-        __syncthreads();
-        if (r < k) {
-            double sum = 0.0;
-            for (int j = r; j < k; ++j) sum = fma(Ts[r * LDP + j], z[j], sum);   // upper triangular T[:k, :k]
-            Ts[r * LDP + k] = -tk * sum;
-        } else if (r == k) {
-            Ts[r * LDP + k] = tk;
-        }
-        __syncthreads();
-    }
-    for (int cidx = 0; cidx < BW; ++cidx) T[r * BW + cidx] = Ts[r * LDP + cidx];
 }
 
 // band storage Bd[j][k] = A[j + k][j], k = 0..BW, for the BW columns that start at j0 (diagonal block from A,
@@ -396,6 +402,7 @@ constexpr int WIN = BW + 1;             // columns a step touches: j .. j + BW
 constexpr int CH = 8;                   // prefetch chunk (columns)
 constexpr int SLOTS = WIN + 2 * CH;     // circular window: live columns + the chunk in flight + the chunk being consumed
 constexpr int RHS_MAX = 48;
+constexpr int RHS_LD = RHS_MAX + 1;      // odd row pitch: a half-warp walking 16 consecutive slots hits 16 banks
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
 {
@@ -405,7 +412,9 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int SOLVE_THREADS = 1024;
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
 band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const double *__restrict__ shifts, const double *__restrict__ rhs_t,
                            int64_t ldr, int nrhs, double *__restrict__ Lg /*[G][m][WIN]*/, double *__restrict__ sol_t, int64_t lds,
                            int *__restrict__ info)
@@ -413,24 +422,25 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
     extern __shared__ double sm[];
     double *win = sm;                                       // SLOTS x WIN: slot (j % SLOTS) holds column j: A[j + k][j], k = 0..BW
     double *rwin = win + SLOTS * WIN;                       // SLOTS x RHS_MAX: right-hand-side rows / solution rows
-    double *lcol = rwin + SLOTS * RHS_MAX;                  // WIN: the finished column of L
+    double *lcol = rwin + SLOTS * RHS_LD;                  // WIN: the finished column of L
     double *ycur = lcol + WIN;                              // RHS_MAX
     const int g = blockIdx.x, t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
     const double shift = shifts[g];
     double *L = Lg + (int64_t)g * m * WIN;
     double *sol = sol_t + (int64_t)g * nrhs * lds;
     int bad = 0;
 
     auto prefetch_columns = [&](int64_t first, int count) {  // asynchronous: band columns + right-hand-side rows
-        for (int idx = t; idx < count * WIN; idx += blockDim.x) {
+        for (int idx = t; idx < count * WIN; idx += SOLVE_THREADS) {
             const int64_t j = first + idx / WIN;
             const int k = idx % WIN;
             if (j < m) cp_async8(&win[(int)(j % SLOTS) * WIN + k], Bd + j * WIN + k);
         }
-        for (int idx = t; idx < count * nrhs; idx += blockDim.x) {
-            const int64_t j = first + idx / nrhs;
-            const int r = idx % nrhs;
-            if (j < m) cp_async8(&rwin[(int)(j % SLOTS) * RHS_MAX + r], rhs_t + (int64_t)r * ldr + j);
+        for (int idx = t; idx < count * RHS_MAX; idx += SOLVE_THREADS) {
+            const int64_t j = first + idx / RHS_MAX;
+            const int r = idx % RHS_MAX;
+            if (j < m && r < nrhs) cp_async8(&rwin[(int)(j % SLOTS) * RHS_LD + r], rhs_t + (int64_t)r * ldr + j);
         }
         cp_async_commit();
     };
@@ -440,44 +450,49 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
     prefetch_columns(WIN + CH, CH);                         // in flight while the first chunk is factorised
 
     // ---- factorisation + forward substitution
-    for (int64_t j = 0; j < m; ++j) {
+    int slot = 0;                                            // j % SLOTS, kept incrementally (32-bit)
+    for (int64_t j = 0; j < m; ++j, slot = (slot + 1 == SLOTS) ? 0 : slot + 1) {
         if (j > 0 && j % CH == 0) {
             // columns up to j + WIN + CH - 1 are needed during this chunk: the group issued one chunk ago has them
             cp_async_wait_all();
             __syncthreads();
             prefetch_columns(j + WIN + CH, CH);              // their slots held columns j - CH .. j - 1 (finished)
         }
-        const int slot = (int)(j % SLOTS);
         const int kn = (int)min((int64_t)BW, m - 1 - j);
         const double d = win[slot * WIN] + shift;
-        const double ljj = sqrt(d);
         if (!(d > 0.0)) bad = 1;
-        const double inv = 1.0 / ljj;
+        const double inv = rsqrt(d);
         if (t <= kn) {
-            const double v = (t == 0) ? ljj : win[slot * WIN + t] * inv;
+            const double v = (t == 0) ? d * inv : win[slot * WIN + t] * inv;
             lcol[t] = v;
             L[j * WIN + t] = v;
         } else if (t < WIN) {
             L[j * WIN + t] = 0.0;
-        }
-        if (t >= 128 && t - 128 < nrhs) {
-            const double y = rwin[slot * RHS_MAX + (t - 128)] * inv;
-            ycur[t - 128] = y;
-            sol[(int64_t)(t - 128) * lds + j] = y;            // y, overwritten by z in the backward pass
+        } else if (t >= 256 && t - 256 < nrhs) {
+            const double y = rwin[slot * RHS_LD + (t - 256)] * inv;
+            ycur[t - 256] = y;
+            sol[(int64_t)(t - 256) * lds + j] = y;            // y, overwritten by z in the backward pass
         }
         __syncthreads();
-        // trailing update of the window: A[j+i][j+l] -= L[i] L[l], 1 <= l <= i <= kn  (slot of column j+l, offset i-l)
-        for (int idx = t; idx < kn * kn; idx += blockDim.x) {
-            const int l = idx / kn + 1, i = idx % kn + 1;
-            if (i >= l) {
-                const int sl = (int)((j + l) % SLOTS);
-                win[sl * WIN + (i - l)] = fma(-lcol[i], lcol[l], win[sl * WIN + (i - l)]);
-            }
+        // trailing update of the window: A[j+i][j+l] -= L[i] L[l], 1 <= l <= i <= kn: warp w takes l = w+1, w+33, ...;
+        // its lanes walk i = l, l+1, ... (contiguous offsets i - l in the slot of column j + l)
+        for (int l = warp + 1; l <= kn; l += SOLVE_THREADS / 32) {
+            int sl = slot + l;
+            if (sl >= SLOTS) sl -= SLOTS;
+            double *col = win + sl * WIN;
+            const double ll = lcol[l];
+            for (int i = l + lane; i <= kn; i += 32) col[i - l] = fma(-lcol[i], ll, col[i - l]);
         }
-        for (int idx = t; idx < kn * nrhs; idx += blockDim.x) {
-            const int i = idx / nrhs + 1, r = idx % nrhs;
-            const int sl = (int)((j + i) % SLOTS);
-            rwin[sl * RHS_MAX + r] = fma(-lcol[i], ycur[r], rwin[sl * RHS_MAX + r]);
+        // right-hand sides: row j+i -= L[i] y      (8 threads per row i, 6 columns each)
+        {
+            const int i = (t >> 3) + 1;
+            if (i <= kn) {
+                int sl = slot + i;
+                if (sl >= SLOTS) sl -= SLOTS;
+                double *row = rwin + sl * RHS_LD;
+                const double li = lcol[i];
+                for (int r = t & 7; r < nrhs; r += 8) row[r] = fma(-li, ycur[r], row[r]);
+            }
         }
         __syncthreads();
     }
@@ -489,21 +504,22 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
     // the factor columns and y rows of chunk c+1 are fetched (cp.async) while chunk c is processed
     double *lring = win;                                    // 2 chunks x CH x WIN   (the window is free now)
     double *yring = win + 2 * CH * WIN;                     // 2 chunks x CH x RHS_MAX
-    double *scratch = yring + 2 * CH * RHS_MAX;             // 256 partial sums
     auto prefetch_back = [&](int64_t top, int buf) {        // columns top, top-1, ..., top-CH+1
-        for (int idx = t; idx < CH * WIN; idx += blockDim.x) {
+        for (int idx = t; idx < CH * WIN; idx += SOLVE_THREADS) {
             const int64_t j = top - idx / WIN;
             if (j >= 0) cp_async8(&lring[(buf * CH + idx / WIN) * WIN + idx % WIN], L + j * WIN + idx % WIN);
         }
-        for (int idx = t; idx < CH * nrhs; idx += blockDim.x) {
-            const int64_t j = top - idx / nrhs;
-            if (j >= 0) cp_async8(&yring[(buf * CH + idx / nrhs) * RHS_MAX + idx % nrhs], sol + (int64_t)(idx % nrhs) * lds + j);
+        for (int idx = t; idx < CH * RHS_MAX; idx += SOLVE_THREADS) {
+            const int64_t j = top - idx / RHS_MAX;
+            const int r = idx % RHS_MAX;
+            if (j >= 0 && r < nrhs) cp_async8(&yring[(buf * CH + idx / RHS_MAX) * RHS_MAX + r], sol + (int64_t)r * lds + j);
         }
         cp_async_commit();
     };
-    __threadfence_block();
     prefetch_back(m - 1, 0);
     int buf = 0;
+    const int r = t >> 4, part = t & 15;                    // 16 lanes per right-hand side share the dot product
+    slot = (int)((m - 1) % SLOTS);                          // slot of column j, kept incrementally while j descends
     for (int64_t top = m - 1; top >= 0; top -= CH, buf ^= 1) {
         cp_async_wait_all();
         __syncthreads();
@@ -513,18 +529,24 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
             if (j < 0) break;
             const int kn = (int)min((int64_t)BW, m - 1 - j);
             const double *lc = lring + (buf * CH + q) * WIN;
-            const int r = t / 5, part = t % 5;               // 5 threads per right-hand side share the dot product
             double sum = 0.0;
-            if (r < nrhs)
-                for (int i = 1 + part; i <= kn; i += 5) sum = fma(lc[i], rwin[(int)((j + i) % SLOTS) * RHS_MAX + r], sum);
-            scratch[t] = sum;
-            __syncthreads();
-            if (t < nrhs) {
-                const double tot = scratch[t * 5] + scratch[t * 5 + 1] + scratch[t * 5 + 2] + scratch[t * 5 + 3] + scratch[t * 5 + 4];
-                const double z = (yring[(buf * CH + q) * RHS_MAX + t] - tot) / lc[0];
-                rwin[(int)(j % SLOTS) * RHS_MAX + t] = z;
-                sol[(int64_t)t * lds + j] = z;
+            if (r < nrhs) {
+                int sl = slot + 1 + part;
+                for (int i = 1 + part; i <= kn; i += 16, sl += 16) {
+                    if (sl >= SLOTS) sl -= SLOTS;
+                    sum = fma(lc[i], rwin[sl * RHS_LD + r], sum);
+                }
             }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            if (part == 0 && r < nrhs) {
+                const double z = (yring[(buf * CH + q) * RHS_MAX + r] - sum) / lc[0];
+                rwin[slot * RHS_LD + r] = z;
+                sol[(int64_t)r * lds + j] = z;
+            }
+            slot = (slot == 0) ? SLOTS - 1 : slot - 1;
             __syncthreads();
         }
     }
@@ -617,7 +639,6 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     double *Vall = reinterpret_cast<double *>(base + p.off_V);
     double *Tall = reinterpret_cast<double *>(base + p.off_T);
     double *R = reinterpret_cast<double *>(base + p.off_R);
-    double *tau = reinterpret_cast<double *>(base + p.off_tau);
     double *Y = reinterpret_cast<double *>(base + p.off_Y);
     double *W = reinterpret_cast<double *>(base + p.off_W);
     double *M1 = reinterpret_cast<double *>(base + p.off_M1);
@@ -650,9 +671,9 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     for (int64_t q = 0; q < p.panels; ++q) {
         const int64_t j0 = q * BW, r0 = j0 + BW, s = m - r0;
         // rows per CTA: at least BW (row k of every step lives in CTA 0), at most what fits shared memory
-        int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, sms), 8));
+        int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, sms - 1), 8));   // one CTA of the grid builds T
         GNNGP_REQUIRE(rows_per <= 208, "band_fit: m = %lld is too large for the shared-memory panel (max ~30 000)", (long long)m);
-        const int n_cta = (int)ceil_div(s, rows_per);
+        const int n_cta = (int)ceil_div(s, rows_per) + 1;
         const size_t smem = (size_t)rows_per * LDP * sizeof(double);
         GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_kernel), 208 * LDP * (int)sizeof(double)));
         GNNGP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
@@ -660,24 +681,19 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
         double *Tq = Tall + q * BW * BW;
         int rows_arg = rows_per;
         int64_t lda_arg = lda, s_arg = s;
-        void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&tau,
+        void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&Tq,
                         (void *)&gbuf, (void *)&rowk, (void *)&counter};
         GNNGP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(sbr_panel_kernel), dim3(n_cta), dim3(256), args, smem, st));
         count_launch();
         band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
         GNNGP_LAUNCHED();
-        // T from V^T V and tau
-        {
-            const int sp = splits_for(BW, BW, s);
-            if (sp > 1) GNNGP_CUDA(cudaMemsetAsync(tmp, 0, (size_t)BW * BW * 8, st));
-            if ((rc = dgemm(BW, BW, s, View{Vp, 1, BW}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, tmp, BW, sp, st)) != GNNGP_OK) return rc;
-            GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(larft_kernel), BW * LDP * (int)sizeof(double)));
-            larft_kernel<<<1, BW, (size_t)BW * LDP * sizeof(double), st>>>(tmp, tau, Tq);
-            GNNGP_LAUNCHED();
-        }
         double *A22 = A + r0 * lda + r0;
-        // Y = A22 V
-        if ((rc = dgemm(s, BW, s, View{A22, lda, 1}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, Y, BW, 1, st)) != GNNGP_OK) return rc;
+        // Y = A22 V   (a skinny output: K is split so that the grid covers the chip)
+        {
+            const int sp = splits_for(s, BW, s);
+            if (sp > 1) GNNGP_CUDA(cudaMemsetAsync(Y, 0, (size_t)s * BW * 8, st));
+            if ((rc = dgemm(s, BW, s, View{A22, lda, 1}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, Y, BW, sp, st)) != GNNGP_OK) return rc;
+        }
         // M1 = V^T Y
         {
             const int sp = splits_for(BW, BW, s);
@@ -703,9 +719,9 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
 
     // ---- one CTA per shift: banded Cholesky + substitutions
     {
-        const size_t smem = (size_t)(SLOTS * WIN + SLOTS * RHS_MAX + WIN + RHS_MAX) * sizeof(double);
+        const size_t smem = (size_t)(SLOTS * WIN + SLOTS * RHS_LD + WIN + RHS_MAX) * sizeof(double);
         GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(band_cholesky_solve_kernel), (int)smem));
-        band_cholesky_solve_kernel<<<(unsigned)G, 256, smem, st>>>(Bd, m, shifts, rhs, m, (int)C, Lg, sol, m, info);
+        band_cholesky_solve_kernel<<<(unsigned)G, SOLVE_THREADS, smem, st>>>(Bd, m, shifts, rhs, m, (int)C, Lg, sol, m, info);
         GNNGP_LAUNCHED();
     }
     // ---- solutions back to the original basis: sol <- sol Q_p^T for p = last .. 0   (x = Q_0 Q_1 ... z)

@@ -555,6 +555,13 @@ class Pipeline(object):
         if m < 2048:
             return "eigh"
         per_rank = (n_nuggets + world - 1) // world
+        if band_ok:
+            # replicated band reduction (every rank solves all nuggets; measured 43 ms at m = 3 053, 111 ms at 6 138,
+            # 0.71 s at 15 405, profiles/r2) against this rank's share of dense factorisations (potrf + substitution:
+            # 1.7 ms at 3 025, 5.2 ms at 6 138, 47 ms at 15 356 per nugget)
+            band_ms = 43.0 * (m / 3053.0) ** 1.75
+            chol_ms = per_rank * 1.7 * (m / 3025.0) ** 2.05
+            return "band" if band_ms <= chol_ms else "cholesky"
         return "cholesky" if per_rank < 30.0 * (m / 3025.0) ** 0.3 else "eigh"
 
     def _fit_by_shifted_solves(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
