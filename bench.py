@@ -227,8 +227,21 @@ def parity_record(ours: dict, ref: dict, source: str) -> dict:
     rec["curve_nuggets_within_2e-3"] = int(sum(bool(all(d[i] <= 2e-3 for d in diffs.values())) for i in range(len(diffs["val"]))))
     rec["curve_val_ours_first_last"] = [round(float(v), 5) for v in list(ours["curves"]["val"][:6]) + list(ours["curves"]["val"][-2:])]
     rec["curve_val_reference_first_last"] = [round(float(v), 5) for v in list(np.asarray(curves["val"])[:6]) + list(np.asarray(curves["val"])[-2:])]
-    rec["ok"] = bool(rec["qqT_rel"] <= 1e-4 and fit_ok and rec.get("argmax_flips_clear_margin", 0) == 0
-                     and rec["metrics_at_selected_nugget_abs_diff"] <= 2e-3 and rec["curve_nuggets_within_2e-3"] >= 0.9 * len(diffs["val"]))
+    if "fit_best64" in ref:
+        rec["ok"] = bool(rec["qqT_rel"] <= 1e-4 and fit_ok and rec.get("argmax_flips_clear_margin", 0) == 0
+                         and rec["metrics_at_selected_nugget_abs_diff"] <= 2e-3 and rec["curve_nuggets_within_2e-3"] >= 0.9 * len(diffs["val"]))
+    else:
+        # fp32-only reference (its fp64 run does not fit the GPU at this size).  Its own accuracy curve collapses at the
+        # smallest nuggets (rounding-noise eigenvalues of its fp32 Gram / fp32 eigh next to -eps d; the fraction-50 golden
+        # shows the same run differing from its fp64 companion by 6e-2 there), so curves are compared on the reference's
+        # PLATEAU (nuggets whose validation accuracy is within 0.01 of its best) and a flip rate of 1e-5 is tolerated.
+        ref_val = np.asarray(curves["val"])
+        plateau = ref_val >= ref_val.max() - 0.01
+        on_plateau = int(sum(bool(all(d[i] <= 2e-3 for d in diffs.values())) for i in range(len(ref_val)) if plateau[i]))
+        rec["reference_plateau_nuggets"] = int(plateau.sum())
+        rec["curve_plateau_nuggets_within_2e-3"] = on_plateau
+        rec["ok"] = bool(rec["qqT_rel"] <= 1e-4 and rec["argmax_flips"] <= max(1, int(1e-5 * flips.size))
+                         and rec["metrics_at_selected_nugget_abs_diff"] <= 2e-3 and on_plateau >= 0.95 * plateau.sum())
     for k in ("qqT_rel", "qqT_rel_fp64", "fit_rel", "fit_rel_nugget_0.1", "curve_max_abs_diff"):
         if k in rec:
             rec[k] = float("%.3e" % rec[k])
@@ -417,7 +430,7 @@ def run_ours(args):
     timer.enabled = False
     table = timer.summary()
     spmm_calls = timer.calls("spmm") + timer.calls("spmm_panels")
-    fit_solver = getattr(getattr(model, "pipe", None), "last_fit_solver", None) or "eigh"
+    fit_solver = getattr(ops, "last_fit_solver", None) or "eigh"
     best = {k: float(summary[k]) for k in ("train", "val", "test", "nugget")}
 
     peaks = load_peaks()

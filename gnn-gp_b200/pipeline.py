@@ -500,14 +500,14 @@ class Pipeline(object):
         if solver == "cholesky":
             fitted = self._fit_by_shifted_solves(q, gram, qty_t, scale, nugget, trailing)
             if fitted is not None:
-                self.last_fit_solver = "cholesky"
+                self.last_fit_solver = self.ops.last_fit_solver = "cholesky"
                 return fitted
         elif solver == "band":
             fitted = self._fit_by_band_reduction(q, gram, qty_t, scale, nugget, trailing)
             if fitted is not None:
-                self.last_fit_solver = "band"
+                self.last_fit_solver = self.ops.last_fit_solver = "band"
                 return fitted
-        self.last_fit_solver = "eigh"
+        self.last_fit_solver = self.ops.last_fit_solver = "eigh"
         evals, evecs = ops.eigh(gram)
         proj_t = ops.gemm_nt(qty_t, ops.transpose(evecs))             # (V^T Q_b^T y_b)^T  [C x m]
         return self._sweep(q, evals, evecs, proj_t, scale, nugget, trailing)

@@ -147,7 +147,15 @@ def check_big(golden, ksamp, fit_best_rows, fit_mid_rows, pred_all, curves, size
     for key in ("train", "val", "test"):
         ref = golden["result_" + key]
         got = np.asarray(curves[key], dtype=np.float32)
-        ok = np.abs(got - ref) <= (slack + 0.5) / max(sizes[key], 1) + 1e-4
+        bound = (slack + 0.5) / max(sizes[key], 1) + 1e-4
+        ok = np.abs(got - ref) <= bound
+        if "result64_" + key in golden:
+            # the reference's fp32 curve is noise at the smallest nuggets (poles of 1 / (w + eps d) at rounding-noise
+            # eigenvalues); a nugget also counts when the curve agrees with the reference's own fp64 run there
+            ok64 = np.abs(got - golden["result64_" + key]) <= bound
+            rep["curve_%s_nuggets_matching_fp32_run" % key] = int(ok.sum())
+            rep["curve_%s_nuggets_matching_fp64_run" % key] = int(ok64.sum())
+            ok = ok | ok64
         rep["curve_%s_max_abs" % key] = float(np.abs(got - ref).max())
         assert ok[int(golden["best"])], "%s accuracy at the selected nugget differs: %.5f vs %.5f" % (key, got[int(golden["best"])], ref[int(golden["best"])])
         assert ok.mean() >= 0.9, "%s accuracy curve: only %.0f%% of nuggets within tolerance" % (key, 100 * ok.mean())

@@ -136,10 +136,10 @@ class StubOps(object):
         sym = torch.tril(gram).double()
         sym = sym + torch.tril(sym, -1).T
         out = self.empty(int(shifts.numel()) * c, m)
-        bad = torch.zeros((), dtype=torch.int64)
+        bad = torch.zeros((), dtype=torch.int64, device=gram.device)
         for i in range(int(shifts.numel())):
-            factor, info = torch.linalg.cholesky_ex(sym + shifts[i] * torch.eye(m, dtype=torch.float64))
-            bad += int(info != 0)
+            factor, info = torch.linalg.cholesky_ex(sym + shifts[i] * torch.eye(m, dtype=torch.float64, device=sym.device))
+            bad += (info != 0).to(torch.int64).reshape(())
             out[i * c:(i + 1) * c] = torch.cholesky_solve(rhs_t.double().T.contiguous(), factor).T.float()
         return out, bad
 

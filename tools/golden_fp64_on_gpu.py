@@ -23,7 +23,7 @@ def main(argv):
         base = dict(np.load(path))
         extra = dict(np.load(os.path.join(ROOT, "gpurun_out", name + "_fp64.npz")))
         assert np.array_equal(base["sample_index"], extra["sample_index"]) and int(base["best"]) == int(extra["best"])
-        for k in ("ksamp64", "fit_best64", "fit_mid64", "pred_best64"):
+        for k in ("ksamp64", "fit_best64", "fit_mid64", "pred_best64", "result64_train", "result64_val", "result64_test"):
             base[k] = extra[k]
         base["fp64_companion_source"] = np.asarray("unmodified reference in float64 on CUDA tensors (tools/golden_fp64_on_gpu.py)")
         np.savez_compressed(path, **base)
@@ -58,6 +58,12 @@ def main(argv):
     out = {"sample_index": golden["sample_index"], "best": golden["best"],
            "ksamp64": (kern[idx] @ kern[idx].T).cpu().numpy(), "fit_best64": fit[best][rows].cpu().numpy(),
            "fit_mid64": fit[50][rows].cpu().numpy(), "pred_best64": torch.argmax(fit[best], 1).cpu().numpy().astype(np.int16)}
+    # accuracy curves of the fp64 run (its own `result` reports R^2 because the targets had to be passed as floats)
+    labels = data.y.to(dev)
+    for key in ("train", "val", "test"):
+        mask = getattr(data, key + "_mask").to(dev)
+        acc = [(torch.argmax(fit[g][mask], 1) == labels[mask]).double().mean().item() for g in range(fit.shape[0])]
+        out["result64_" + key] = np.asarray(acc, dtype=np.float32)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", name + "_fp64.npz"), **out)
     print("wrote gpurun_out/%s_fp64.npz; peak GPU memory %.1f GB" % (name, torch.cuda.max_memory_allocated() / 1e9))
