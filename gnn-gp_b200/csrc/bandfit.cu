@@ -20,6 +20,8 @@
 // Everything is fp64 (the nugget 1e-3 d sits ~1e-8 below the largest eigenvalue of G; fp32 would not resolve it).
 // A non-positive pivot (rounding noise of the fp32 Gram above the smallest shift) is counted in `info`; the caller
 // then falls back to the eigen route, which tolerates an indefinite matrix.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -35,18 +37,31 @@ constexpr int LDP = BW + 1;             // padded slab row (bank-conflict-free c
 // generic fp64 GEMM on the fp64 tensor path (mma.sync m8n8k4):  C = alpha * (A1 B1 + A2 B2) + beta * C   (or atomic
 // accumulation for split-K).  Operands are strided views: A(i, k) = p[i * rs + k * cs], B(k, j) = p[k * rs + j * cs];
 // one of the two strides of every operand is 1.  CTA tile 128 x 64, K steps of 16, 8 warps of 32 x 32 (4 x 4 DMMA
-// fragments each: 16 FMA per double read from shared memory — the CUDA-core version with an 8 x 4 register tile read
-// 96 B per 32 FMA and was shared-memory-bound at 13.6 TFLOP/s).  Both operand tiles sit in shared memory as
-// [row][k] with a row pitch of 20 doubles: the fragment loads of a half-warp (4 rows x 4 k) hit 16 distinct banks.
+// fragments each: 16 FMA per double read from shared memory — a CUDA-core version with an 8 x 4 register tile read
+// 96 B per 32 FMA and was shared-memory-bound at 13.6 TFLOP/s).  Operand tiles arrive through a 3-stage cp.async
+// ring (one __syncthreads per K step); a tile keeps the memory order of its source — [row][k] (pitch 20) for a
+// k-contiguous operand, [k][row] (pitch 132 / 68) for a row-contiguous one — and both pitches are 4 mod 16 doubles,
+// so the fragment loads of a half-warp (4 rows x 4 k) hit 16 distinct banks either way.
 // ---------------------------------------------------------------------------------------------
 struct View { const double *p; int64_t rs, cs; };
 
-constexpr int GM = 128, GN = 64, GK = 16, GLD = GK + 4;
+constexpr int GM = 128, GN = 64, GK = 16;
+constexpr int G_STAGES = 3;
+constexpr int GA_DOUBLES = GM * (GK + 4);                  // 2560 >= GK * (GM + 4)
+constexpr int GB_DOUBLES = GN * (GK + 4);                  // 1280 >= GK * (GN + 4)
+constexpr int G_SMEM = G_STAGES * (GA_DOUBLES + GB_DOUBLES) * 8;
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+// 8-byte asynchronous copy; `ok == false` zero-fills the destination (src-size 0) without touching memory
+__device__ __forceinline__ void cp_async8_zfill(double *smem_dst, const double *gmem_src, bool ok)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    const int bytes = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
 }
 
 template <bool ATOMIC>
@@ -54,8 +69,7 @@ __global__ void __launch_bounds__(256, 2)
 dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1, View B1, View A2, View B2, double beta,
              double *__restrict__ C, int64_t ldc, int splits)
 {
-    __shared__ __align__(16) double As[GM][GLD];
-    __shared__ __align__(16) double Bs[GN][GLD];
+    extern __shared__ __align__(16) double gsm[];
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
     const int g = lane >> 2, t4 = lane & 3;                 // fragment coordinates
@@ -73,81 +87,81 @@ dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    double ra[8], rb[4];
-    auto fetch = [&](int64_t kt) {
-        const bool second = kt >= tiles1;
-        const View A = second ? A2 : A1, B = second ? B2 : B1;
-        const int64_t K = second ? K2 : K1;
-        const int64_t k0 = (second ? kt - tiles1 : kt) * GK;
-        if (A.cs == 1) {                                    // k-contiguous rows
-            const int kk = t & 15;
+    auto issue = [&](int64_t kt) {                          // tile kt -> stage (kt - t_begin) % G_STAGES
+        if (kt < t_end) {
+            const int st = (int)((kt - t_begin) % G_STAGES);
+            double *As = gsm + st * (GA_DOUBLES + GB_DOUBLES);
+            double *Bs = As + GA_DOUBLES;
+            const bool second = kt >= tiles1;
+            const View A = second ? A2 : A1, B = second ? B2 : B1;
+            const int64_t K = second ? K2 : K1;
+            const int64_t k0 = (second ? kt - tiles1 : kt) * GK;
+            if (A.cs == 1) {                                // k-contiguous rows -> [row][k]
+                const int kk = t & 15;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int64_t row = m0 + (t >> 4) + 16 * r;
-                ra[r] = (row < M && k0 + kk < K) ? __ldg(A.p + row * A.rs + (k0 + kk)) : 0.0;
+                for (int r = 0; r < 8; ++r) {
+                    const int rl = (t >> 4) + 16 * r;
+                    const bool ok = (m0 + rl < M) && (k0 + kk < K);
+                    cp_async8_zfill(As + rl * (GK + 4) + kk, ok ? A.p + (m0 + rl) * A.rs + (k0 + kk) : A.p, ok);
+                }
+            } else {                                        // row-contiguous columns -> [k][row]
+                const int mm = t & 127;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int kk = (t >> 7) + 2 * r;
+                    const bool ok = (m0 + mm < M) && (k0 + kk < K);
+                    cp_async8_zfill(As + kk * (GM + 4) + mm, ok ? A.p + (m0 + mm) * A.rs + (k0 + kk) * A.cs : A.p, ok);
+                }
             }
-        } else {                                            // m-contiguous columns
-            const int mm = t & 127;
+            if (B.cs == 1) {                                // n-contiguous rows of B -> [k][n]
+                const int jj = t & 63;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int64_t kk = (t >> 7) + 2 * r;
-                ra[r] = (m0 + mm < M && k0 + kk < K) ? __ldg(A.p + (m0 + mm) * A.rs + (k0 + kk) * A.cs) : 0.0;
+                for (int r = 0; r < 4; ++r) {
+                    const int kk = (t >> 6) + 4 * r;
+                    const bool ok = (n0 + jj < N) && (k0 + kk < K);
+                    cp_async8_zfill(Bs + kk * (GN + 4) + jj, ok ? B.p + (k0 + kk) * B.rs + (n0 + jj) : B.p, ok);
+                }
+            } else {                                        // k-contiguous (B given as rows of B^T) -> [n][k]
+                const int kk = t & 15;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int jl = (t >> 4) + 16 * r;
+                    const bool ok = (n0 + jl < N) && (k0 + kk < K);
+                    cp_async8_zfill(Bs + jl * (GK + 4) + kk, ok ? B.p + (k0 + kk) * B.rs + (n0 + jl) * B.cs : B.p, ok);
+                }
             }
         }
-        if (B.cs == 1) {                                    // n-contiguous rows of B
-            const int jj = t & 63;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int64_t kk = (t >> 6) + 4 * r;
-                rb[r] = (n0 + jj < N && k0 + kk < K) ? __ldg(B.p + (k0 + kk) * B.rs + (n0 + jj)) : 0.0;
-            }
-        } else {                                            // k-contiguous (B given as rows of B^T)
-            const int kk = t & 15;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int64_t jj = (t >> 4) + 16 * r;
-                rb[r] = (n0 + jj < N && k0 + kk < K) ? __ldg(B.p + (k0 + kk) * B.rs + (n0 + jj) * B.cs) : 0.0;
-            }
-        }
-    };
-    auto stash = [&](int64_t kt) {
-        const bool second = kt >= tiles1;
-        const View A = second ? A2 : A1, B = second ? B2 : B1;
-        if (A.cs == 1) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) As[(t >> 4) + 16 * r][t & 15] = ra[r];
-        } else {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) As[t & 127][(t >> 7) + 2 * r] = ra[r];
-        }
-        if (B.cs == 1) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) Bs[t & 63][(t >> 6) + 4 * r] = rb[r];
-        } else {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) Bs[(t >> 4) + 16 * r][t & 15] = rb[r];
-        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the wait arithmetic uniform)
     };
 
-    fetch(t_begin);
+#pragma unroll
+    for (int sidx = 0; sidx < G_STAGES - 1; ++sidx) issue(t_begin + sidx);
     for (int64_t kt = t_begin; kt < t_end; ++kt) {
-        __syncthreads();
-        stash(kt);
-        __syncthreads();
-        if (kt + 1 < t_end) fetch(kt + 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(G_STAGES - 2) : "memory");
+        __syncthreads();                                    // tile kt landed for everyone; stage of tile kt-1 is free
+        issue(kt + G_STAGES - 1);
+        const int st = (int)((kt - t_begin) % G_STAGES);
+        const double *As = gsm + st * (GA_DOUBLES + GB_DOUBLES);
+        const double *Bs = As + GA_DOUBLES;
+        const bool second = kt >= tiles1;
+        const bool a_rows = (second ? A2.cs : A1.cs) == 1;  // [row][k] layout
+        const bool b_cols = (second ? B2.cs : B1.cs) == 1;  // [k][n] layout
 #pragma unroll
         for (int k4 = 0; k4 < GK; k4 += 4) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[wm + i * 8 + g][k4 + t4];
+            for (int i = 0; i < 4; ++i)
+                a[i] = a_rows ? As[(wm + i * 8 + g) * (GK + 4) + k4 + t4] : As[(k4 + t4) * (GM + 4) + wm + i * 8 + g];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[wn + j * 8 + g][k4 + t4];
+            for (int j = 0; j < 4; ++j)
+                b[j] = b_cols ? Bs[(k4 + t4) * (GN + 4) + wn + j * 8 + g] : Bs[(wn + j * 8 + g) * (GK + 4) + k4 + t4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t row = m0 + wm + i * 8 + g;
@@ -174,8 +188,13 @@ static int dgemm(int64_t M, int64_t N, int64_t K1, View A1, View B1, int64_t K2,
 {
     if (M <= 0 || N <= 0) return GNNGP_OK;
     const dim3 grid((unsigned)ceil_div(N, GN), (unsigned)ceil_div(M, GM), (unsigned)std::max(1, splits));
-    if (splits > 1) dgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K1, K2, alpha, A1, B1, A2, B2, beta, C, ldc, splits);
-    else dgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K1, K2, alpha, A1, B1, A2, B2, beta, C, ldc, 1);
+    if (splits > 1) {
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(dgemm_kernel<true>), G_SMEM));
+        dgemm_kernel<true><<<grid, 256, G_SMEM, st>>>(M, N, K1, K2, alpha, A1, B1, A2, B2, beta, C, ldc, splits);
+    } else {
+        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(dgemm_kernel<false>), G_SMEM));
+        dgemm_kernel<false><<<grid, 256, G_SMEM, st>>>(M, N, K1, K2, alpha, A1, B1, A2, B2, beta, C, ldc, 1);
+    }
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }
@@ -350,6 +369,131 @@ sbr_panel_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows
     }
     if (blockIdx.x == 0)
         for (int64_t gi = s + h; gi < BW; gi += 2) R[gi * BW + c] = 0.0;     // panels shorter than BW rows
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same factorisation for panels of up to 15 x 208 rows as ONE thread-block cluster (up to 16 CTAs): the per-step
+// reduction goes through distributed shared memory and the hardware cluster barrier instead of global atomics and a
+// global-memory barrier (measured: 7.5 us per column step for the grid version at 24 CTAs, bound by the barrier
+// round trips and the post-barrier L2 loads).  CTA r < n_slab publishes its partial dot products in its own shared
+// memory; after cluster.sync() every CTA sums the partials of all ranks with remote (DSMEM) loads.  CTA 0 also
+// publishes row k; the last CTA of the cluster builds T as in the grid version.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+sbr_panel_cluster_kernel(const double *__restrict__ Ap, int64_t lda, int64_t s, int rows_per, double *__restrict__ V,
+                         double *__restrict__ R, double *__restrict__ T)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double slab[];                        // rows_per x LDP (slab CTAs) / BW x LDP (the T CTA)
+    __shared__ double part[2][BW];                          // this CTA's partial dots, double-buffered by step parity
+    __shared__ double rowk_s[2][BW];                        // row k of the panel (meaningful in CTA 0)
+    __shared__ double w_s[BW];
+    __shared__ double red[2][BW];
+    const int t = threadIdx.x;
+    const int c = t & (BW - 1), h = t >> 7;
+    const int rank = (int)cluster.block_rank(), n_rank = (int)cluster.num_blocks();
+    const int n_slab = n_rank - 1;
+    const bool t_cta = rank == n_slab;
+    const int64_t row0 = (int64_t)rank * rows_per;
+    const int nrows = t_cta ? 0 : (int)max((int64_t)0, min((int64_t)rows_per, s - row0));
+
+    if (t_cta) {
+        for (int i = h; i < BW; i += 2) slab[i * LDP + c] = 0.0;
+    } else {
+        for (int i = h; i < nrows; i += 2) slab[i * LDP + c] = Ap[(row0 + i) * lda + c];
+    }
+    const int steps = (int)min((int64_t)BW, s);
+    const double *rowk_remote = cluster.map_shared_rank(&rowk_s[0][0], 0);
+    __syncthreads();
+
+    for (int k = 0; k < steps; ++k) {
+        const int par = k & 1;
+        // ---- pass 1: partial dots of column k (rows >= k) with every column, into this CTA's shared memory
+        if (!t_cta) {
+            const int lo = (int)max((int64_t)0, (int64_t)k - row0);
+            double p0 = 0.0, p1 = 0.0;
+            int i = lo + h;
+            for (; i + 2 < nrows; i += 4) {
+                p0 = fma(slab[i * LDP + c], slab[i * LDP + k], p0);
+                p1 = fma(slab[(i + 2) * LDP + c], slab[(i + 2) * LDP + k], p1);
+            }
+            for (; i < nrows; i += 2) p0 = fma(slab[i * LDP + c], slab[i * LDP + k], p0);
+            red[h][c] = p0 + p1;
+            __syncthreads();
+            if (h == 0) {
+                part[par][c] = red[0][c] + red[1][c];
+                if (rank == 0) rowk_s[par][c] = slab[k * LDP + c];
+            }
+        }
+        cluster.sync();
+        // ---- pass 2: sum the partials of all slab CTAs (remote shared memory), derive the reflector
+        {
+            double sum = 0.0;
+            for (int r = h; r < n_slab; r += 2) sum += *(cluster.map_shared_rank(&part[par][c], r));
+            red[h][c] = sum;
+            if (h == 0) w_s[c] = rowk_remote[par * BW + c];
+        }
+        __syncthreads();
+        const double nrm2 = red[0][k] + red[1][k], x0 = w_s[k];
+        const double gc = red[0][c] + red[1][c], rc = w_s[c];
+        const bool live = nrm2 > 0.0;
+        double alpha = x0, inv_v0 = 1.0, tau = 0.0;
+        if (live) {
+            const double nrm = sqrt(nrm2);
+            alpha = x0 >= 0.0 ? -nrm : nrm;
+            inv_v0 = 1.0 / (x0 - alpha);
+            tau = (alpha - x0) / alpha;
+        }
+        const double wc = live ? (gc - alpha * rc) * inv_v0 : 0.0;        // w[c] (c > k) and z[c] (c < k)
+        __syncthreads();                                                   // red / w_s are reused below
+        if (t_cta) {
+            if (h == 0) w_s[c] = (c < k) ? wc : 0.0;
+            __syncthreads();
+            if (c < k) {
+                double sum = 0.0;
+                for (int j = c + h; j < k; j += 2) sum = fma(slab[c * LDP + j], w_s[j], sum);
+                red[h][c] = sum;
+            }
+            __syncthreads();
+            if (h == 0) {
+                if (c < k) slab[c * LDP + k] = -tau * (red[0][c] + red[1][c]);
+                else if (c == k) slab[c * LDP + k] = tau;
+            }
+            __syncthreads();
+            continue;
+        }
+        if (live) {
+            const int lo = (int)max((int64_t)0, (int64_t)k + 1 - row0);
+            if (c > k) {
+                const double f = -tau * inv_v0 * wc;
+                for (int i = lo + h; i < nrows; i += 2) slab[i * LDP + c] = fma(slab[i * LDP + k], f, slab[i * LDP + c]);
+                if (rank == 0 && h == 0) slab[k * LDP + c] = fma(-tau, wc, slab[k * LDP + c]);
+            }
+            __syncthreads();
+            if (c == k) {
+                for (int i = lo + h; i < nrows; i += 2) slab[i * LDP + k] *= inv_v0;
+                if (rank == 0 && h == 0) slab[k * LDP + k] = alpha;
+            }
+        }
+        __syncthreads();
+    }
+    if (t_cta) {
+        for (int i = h; i < BW; i += 2) T[i * BW + c] = slab[i * LDP + c];
+    } else {
+        for (int i = h; i < nrows; i += 2) {
+            const int64_t gi = row0 + i;
+            double v = slab[i * LDP + c];
+            if (c >= steps) v = 0.0;
+            else if (gi < c) v = 0.0;
+            else if (gi == c) v = 1.0;
+            V[gi * BW + c] = v;
+            if (gi < BW) R[gi * BW + c] = (gi <= c && gi < steps) ? slab[i * LDP + c] : 0.0;
+        }
+        if (rank == 0)
+            for (int64_t gi = s + h; gi < BW; gi += 2) R[gi * BW + c] = 0.0;
+    }
+    cluster.sync();                                          // no CTA may exit while a peer still reads its shared memory
 }
 
 // band storage Bd[j][k] = A[j + k][j], k = 0..BW, for the BW columns that start at j0 (diagonal block from A,
@@ -668,23 +812,54 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     GNNGP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     GNNGP_REQUIRE(coop, "band_fit: the device does not support cooperative launches");
     double *Vp = Vall;
+    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_kernel), 208 * LDP * (int)sizeof(double)));
+    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_cluster_kernel), 208 * LDP * (int)sizeof(double)));
+    bool cluster_ok = cudaFuncSetAttribute(sbr_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     for (int64_t q = 0; q < p.panels; ++q) {
         const int64_t j0 = q * BW, r0 = j0 + BW, s = m - r0;
-        // rows per CTA: at least BW (row k of every step lives in CTA 0), at most what fits shared memory
-        int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, sms - 1), 8));   // one CTA of the grid builds T
-        GNNGP_REQUIRE(rows_per <= 208, "band_fit: m = %lld is too large for the shared-memory panel (max ~30 000)", (long long)m);
-        const int n_cta = (int)ceil_div(s, rows_per) + 1;
-        const size_t smem = (size_t)rows_per * LDP * sizeof(double);
-        GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_kernel), 208 * LDP * (int)sizeof(double)));
-        GNNGP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
         const double *Ap = A + r0 * lda + j0;
         double *Tq = Tall + q * BW * BW;
-        int rows_arg = rows_per;
         int64_t lda_arg = lda, s_arg = s;
-        void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&Tq,
-                        (void *)&gbuf, (void *)&rowk, (void *)&counter};
-        GNNGP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(sbr_panel_kernel), dim3(n_cta), dim3(256), args, smem, st));
-        count_launch();
+        bool done = false;
+        if (s <= 15 * 208 && cluster_ok) {
+            // one thread-block cluster: up to 15 slab CTAs + the CTA that builds T
+            int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, 15), 8));
+            const int n_cta = (int)ceil_div(s, rows_per) + 1;
+            const size_t smem = (size_t)rows_per * LDP * sizeof(double);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(n_cta);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = n_cta;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const cudaError_t err = cudaLaunchKernelEx(&cfg, sbr_panel_cluster_kernel, Ap, lda_arg, s_arg, rows_per, Vp, R, Tq);
+            if (err == cudaSuccess) {
+                count_launch();
+                done = true;
+            } else {
+                (void)cudaGetLastError();                   // e.g. the cluster does not fit this device: use the grid version
+                cluster_ok = false;
+            }
+        }
+        if (!done) {
+            // cooperative grid.  rows per CTA: at least BW (row k of every step lives in CTA 0), at most what fits shared memory
+            int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, sms - 1), 8));   // one CTA of the grid builds T
+            GNNGP_REQUIRE(rows_per <= 208, "band_fit: m = %lld is too large for the shared-memory panel (max ~30 000)", (long long)m);
+            const int n_cta = (int)ceil_div(s, rows_per) + 1;
+            const size_t smem = (size_t)rows_per * LDP * sizeof(double);
+            GNNGP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+            int rows_arg = rows_per;
+            void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&Tq,
+                            (void *)&gbuf, (void *)&rowk, (void *)&counter};
+            GNNGP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(sbr_panel_kernel), dim3(n_cta), dim3(256), args, smem, st));
+            count_launch();
+        }
         band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
         GNNGP_LAUNCHED();
         double *A22 = A + r0 * lda + r0;
