@@ -51,10 +51,14 @@ constexpr int GA_DOUBLES = GM * (GK + 4);                  // 2560 >= GK * (GM +
 constexpr int GB_DOUBLES = GN * (GK + 4);                  // 1280 >= GK * (GN + 4)
 constexpr int G_SMEM = G_STAGES * (GA_DOUBLES + GB_DOUBLES) * 8;
 
-__device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
+// D (16 x 8) += A (16 x 8, row) * B (8 x 8, col).  Fragments (g = lane / 4, q = lane % 4):
+//   a0 = A[g][q], a1 = A[g + 8][q], a2 = A[g][q + 4], a3 = A[g + 8][q + 4];  b0 = B[q][g], b1 = B[q + 4][g];
+//   d0, d1 = D[g][2q], D[g][2q + 1];  d2, d3 = D[g + 8][2q], D[g + 8][2q + 1]
+__device__ __forceinline__ void dmma16x8x8(double (&d)[4], const double (&a)[4], const double (&b)[2])
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 // 8-byte asynchronous copy; `ok == false` zero-fills the destination (src-size 0) without touching memory
 __device__ __forceinline__ void cp_async8_zfill(double *smem_dst, const double *gmem_src, bool ok)
@@ -81,11 +85,11 @@ dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1
     const int64_t t_begin = (int64_t)blockIdx.z * per, t_end = min(tiles, t_begin + per);
     if (t_begin >= t_end) return;
 
-    double acc[4][4][2];
+    double acc[2][4][4];                                    // 2 x 4 fragments of 16 x 8
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0;
 
     auto issue = [&](int64_t kt) {                          // tile kt -> stage (kt - t_begin) % G_STAGES
         if (kt < t_end) {
@@ -146,35 +150,47 @@ dgemm_kernel(int64_t M, int64_t N, int64_t K1, int64_t K2, double alpha, View A1
         const bool second = kt >= tiles1;
         const bool a_rows = (second ? A2.cs : A1.cs) == 1;  // [row][k] layout
         const bool b_cols = (second ? B2.cs : B1.cs) == 1;  // [k][n] layout
+        auto a_at = [&](int row, int k) { return a_rows ? As[row * (GK + 4) + k] : As[k * (GM + 4) + row]; };
+        auto b_at = [&](int k, int col) { return b_cols ? Bs[k * (GN + 4) + col] : Bs[col * (GK + 4) + k]; };
 #pragma unroll
-        for (int k4 = 0; k4 < GK; k4 += 4) {
-            double a[4], b[4];
+        for (int k8 = 0; k8 < GK; k8 += 8) {
+            double a[2][4], b[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                a[i] = a_rows ? As[(wm + i * 8 + g) * (GK + 4) + k4 + t4] : As[(k4 + t4) * (GM + 4) + wm + i * 8 + g];
+            for (int i = 0; i < 2; ++i) {
+                const int row = wm + i * 16 + g;
+                a[i][0] = a_at(row, k8 + t4);     a[i][1] = a_at(row + 8, k8 + t4);
+                a[i][2] = a_at(row, k8 + t4 + 4); a[i][3] = a_at(row + 8, k8 + t4 + 4);
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                b[j] = b_cols ? Bs[(k4 + t4) * (GN + 4) + wn + j * 8 + g] : Bs[(wn + j * 8 + g) * (GK + 4) + k4 + t4];
+            for (int j = 0; j < 4; ++j) {
+                const int col = wn + j * 8 + g;
+                b[j][0] = b_at(k8 + t4, col);
+                b[j][1] = b_at(k8 + t4 + 4, col);
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma16x8x8(acc[i][j], a[i], b[j]);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t row = m0 + wm + i * 8 + g;
-        if (row >= M) continue;
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int hh = 0; hh < 2; ++hh) {
+            const int64_t row = m0 + wm + i * 16 + hh * 8 + g;
+            if (row >= M) continue;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int64_t col = n0 + wn + j * 8 + t4 * 2 + e;
-                if (col >= N) continue;
-                double *c = C + row * ldc + col;
-                if (ATOMIC) atomicAdd(c, alpha * acc[i][j][e]);
-                else *c = (beta == 0.0) ? alpha * acc[i][j][e] : fma(beta, *c, alpha * acc[i][j][e]);
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t col = n0 + wn + j * 8 + t4 * 2 + e;
+                    if (col >= N) continue;
+                    double *c = C + row * ldc + col;
+                    const double v = alpha * acc[i][j][hh * 2 + e];
+                    if (ATOMIC) atomicAdd(c, v);
+                    else *c = (beta == 0.0) ? v : fma(beta, *c, v);
+                }
             }
         }
     }
@@ -204,7 +220,7 @@ static int splits_for(int64_t M, int64_t N, int64_t K)
 {
     const int64_t tiles = ceil_div(M, GM) * ceil_div(N, GN);
     const int64_t ktiles = ceil_div(K, GK);
-    int64_t s = std::min<int64_t>(ktiles / 4, (2 * (int64_t)sm_count()) / std::max<int64_t>(tiles, 1));
+    int64_t s = std::min<int64_t>(ktiles / 4, (4 * (int64_t)sm_count()) / std::max<int64_t>(tiles, 1));
     return (int)std::max<int64_t>(1, std::min<int64_t>(s, 512));
 }
 

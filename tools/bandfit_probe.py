@@ -27,7 +27,10 @@ def timeit(fn, reps=2):
     return a.elapsed_time(b) / reps, r
 
 
+ONLY = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 for m, nt in ((3053, 40000), (6138, 40000), (15405, 40000)):
+    if ONLY and m != ONLY:
+        continue
     if len(sys.argv) > 1 and m > int(sys.argv[1]):
         continue
     gen = torch.Generator(device=dev).manual_seed(m)
