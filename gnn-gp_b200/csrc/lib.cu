@@ -1,5 +1,6 @@
 // Library-level entry points: error text, device info, engine switch, launch counter.
 #include <stdarg.h>
+#include <string.h>
 #include <atomic>
 #include <mutex>
 #include <set>
@@ -79,5 +80,57 @@ int gnngp_set_gemm_engine(int engine)
 }
 
 int64_t gnngp_launch_count(void) { return gnngp::g_launches.load(); }
+
+
+// ---- peer exchange buffers (CUDA IPC), see include/gnngp_b200.h
+int64_t gnngp_exchange_alloc(size_t bytes, void *handle_out)
+{
+    void *ptr = nullptr;
+    if (!handle_out || bytes == 0 || cudaMalloc(&ptr, bytes) != cudaSuccess) {
+        gnngp::set_error("exchange_alloc: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    cudaIpcMemHandle_t handle;
+    if (cudaIpcGetMemHandle(&handle, ptr) != cudaSuccess) {
+        gnngp::set_error("exchange_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(ptr);
+        return 0;
+    }
+    memcpy(handle_out, &handle, sizeof(handle));
+    return (int64_t)reinterpret_cast<uintptr_t>(ptr);
+}
+
+int64_t gnngp_exchange_open(const void *handle_in)
+{
+    cudaIpcMemHandle_t handle;
+    memcpy(&handle, handle_in, sizeof(handle));
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        gnngp::set_error("exchange_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    return (int64_t)reinterpret_cast<uintptr_t>(ptr);
+}
+
+int gnngp_exchange_close(int64_t peer_ptr)
+{
+    GNNGP_CUDA(cudaIpcCloseMemHandle(reinterpret_cast<void *>((uintptr_t)peer_ptr)));
+    return GNNGP_OK;
+}
+
+int gnngp_exchange_free(int64_t ptr)
+{
+    GNNGP_CUDA(cudaFree(reinterpret_cast<void *>((uintptr_t)ptr)));
+    return GNNGP_OK;
+}
+
+int gnngp_copy2d_f32(const float *src, int64_t lds, int64_t rows, int64_t cols, int64_t dst_ptr, int64_t ldd, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(src && dst_ptr && rows >= 0 && cols >= 0 && lds >= cols && ldd >= cols, "copy2d: bad arguments");
+    if (rows == 0 || cols == 0) return GNNGP_OK;
+    GNNGP_CUDA(cudaMemcpy2DAsync(reinterpret_cast<void *>((uintptr_t)dst_ptr), (size_t)ldd * sizeof(float), src, (size_t)lds * sizeof(float),
+                                 (size_t)cols * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice, gnngp::as_stream(stream)));
+    return GNNGP_OK;
+}
 
 }  // extern "C"

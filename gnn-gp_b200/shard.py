@@ -46,44 +46,72 @@ class TorchComm(object):
         self.bytes_gathered = 0
         self.bytes_reduced = 0
         self.bytes_pulled = 0
-        # fused peer-memory gather (NVLink P2P loads inside our own kernel) instead of an NCCL all-gather;
-        # needs torch symmetric memory on an NCCL group.  Opt-in (GNNGP_PEER_GATHER=1): measured 0.2180 s vs
-        # 0.2209 s per step at N = 2 (profiles/r1/call13_*), parity-checked at N = 2 and run at N = 8 for the
-        # fraction-50 workload, but a fraction-10 run at N = 8 did not finish inside its time limit with it
-        # enabled (cause not yet isolated), so NCCL stays the default exchange.
+        # Fused all-gather + panel layout over peer memory (NVLink P2P loads inside our own kernel) instead of an NCCL
+        # all-gather into a staging buffer followed by the panel copy.  Exchange buffers are plain device allocations
+        # shared through CUDA IPC (gnngp_exchange_*); the two cross-rank ordering points per exchange are one-element
+        # NCCL all-reduces, which are stream-ordered — no symmetric-memory rendezvous (round 1's torch
+        # symmetric-memory version stalled with 7 GB blocks).  GNNGP_PEER_GATHER=1 turns it on (dense-row graphs, NCCL).
         self.peer_gather = (os.environ.get("GNNGP_PEER_GATHER", "0") == "1" and torch.cuda.is_available()
                             and dist.get_backend(group) == "nccl")
-        self._symm = {}
+        self._exchange = {}
+        self._token = None
 
-    def _symmetric_block(self, rows: int, ld: int, device):
+    def _exchange_block(self, ops, rows: int, ld: int, device):
+        """This rank's exchange buffer for [rows x ld] fp32 blocks and a device table of all ranks' pointers."""
         key = (rows, ld)
-        if key not in self._symm:
-            import torch.distributed._symmetric_memory as symm_mem
-            buf = symm_mem.empty((rows, ld), dtype=torch.float32, device=device)
-            handle = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-            self._symm[key] = (buf, handle)
-        return self._symm[key]
+        hit = self._exchange.get(key)
+        if hit is None:
+            import ctypes
+            with torch.cuda.device(device):
+                handle = ctypes.create_string_buffer(64)
+                mine = int(ops.lib.query("gnngp_exchange_alloc", rows * ld * 4, ctypes.addressof(handle)))
+                ok = torch.tensor([1 if mine else 0], device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # every rank takes the same branch
+                if int(ok) == 0:
+                    raise RuntimeError("exchange buffer allocation failed on some rank: %s" % ops.lib.last_error())
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+                ptrs = []
+                for r, raw in enumerate(handles):
+                    if r == self.rank:
+                        ptrs.append(mine)
+                    else:
+                        peer = int(ops.lib.query("gnngp_exchange_open", raw))
+                        if not peer:
+                            raise RuntimeError("cudaIpcOpenMemHandle failed for rank %d: %s" % (r, ops.lib.last_error()))
+                        ptrs.append(peer)
+                table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+            hit = (mine, table)
+            self._exchange[key] = hit
+        return hit
+
+    def _stream_barrier(self, device) -> None:
+        """Cross-rank ordering point on the current stream: a one-element NCCL all-reduce."""
+        if self._token is None:
+            self._token = torch.zeros(1, device=device)
+        dist.all_reduce(self._token, group=self.group)
 
     def pull_panels(self, ops, block: Tensor, layout: RowLayout):
-        """Fused all-gather + panel layout for the sparse product: every rank publishes its row block in a
-        symmetric-memory buffer, then ONE kernel per rank pulls all blocks over NVLink straight into the
-        64-column panels its SpMM gathers from (no gathered [N x k] buffer, no NCCL call).  Returns
-        (workspace tensor, panel pointer) or None when symmetric memory is unavailable (→ NCCL all-gather)."""
+        """Fused all-gather + panel layout for the sparse product: every rank publishes its row block in its
+        exchange buffer, then ONE kernel per rank (``panelize_peers_kernel``) pulls all blocks over NVLink straight
+        into the 64-column panels its SpMM gathers from (no gathered [N x k] buffer, no NCCL data movement).
+        Returns (workspace tensor, panel pointer) or None when peer memory is unavailable (→ NCCL all-gather)."""
         if not self.peer_gather:
             return None
         n_local, k = block.shape
         ld = _round_up(max(k, 1), 4)
         try:
-            buf, handle = self._symmetric_block(layout.rows_per_rank, ld, block.device)
-        except Exception as exc:           # same environment on every rank: all of them land here together
-            warnings.warn("gnngp_b200: symmetric memory unavailable (%r); using the NCCL all-gather" % (exc,))
+            mine, table = self._exchange_block(ops, layout.rows_per_rank, ld, block.device)
+        except RuntimeError as exc:        # raised on every rank alike (the allocation outcome is all-reduced)
+            warnings.warn("gnngp_b200: peer exchange buffers unavailable (%s); using the NCCL all-gather" % (exc,))
             self.peer_gather = False
             return None
-        buf[:n_local, :k].copy_(block)
-        handle.barrier(channel=0)                          # every rank's block is published
-        ws, ptr = ops.panels_from_peers(handle.buffer_ptrs_dev, self.world, layout.rows_per_rank, ld, layout.n, k,
-                                        block.device)
-        handle.barrier(channel=1)                          # every rank has finished reading before a block is reused
+        src = block if (k <= 1 or block.stride(1) == 1) else block.contiguous()
+        ops.lib.call("gnngp_copy2d_f32", src.data_ptr(), int(src.stride(0)) if n_local > 1 else max(k, 1), n_local, k, mine, ld,
+                     torch.cuda.current_stream(block.device).cuda_stream)
+        self._stream_barrier(block.device)                 # every rank's block is published
+        ws, ptr = ops.panels_from_peers(table.data_ptr(), self.world, layout.rows_per_rank, ld, layout.n, k, block.device)
+        self._stream_barrier(block.device)                 # every rank has finished reading before a block is reused
         self.bytes_pulled += (self.world - 1) * layout.rows_per_rank * k * 4
         return ws, ptr
 

@@ -194,6 +194,18 @@ int gnngp_argmax_count(const float *fitted, const int64_t *y, const uint8_t *mem
 int gnngp_sqerr_sum(const float *fitted, const float *y, const uint8_t *membership, int64_t G, int64_t n,
                     int64_t k, double *sse, gnngp_stream_t stream);
 
+/* ---- peer exchange buffers for the fused all-gather + panel layout (sharded mode) ---------------------------
+ * Plain device allocations that other ranks of the same node map through CUDA IPC, so that gnngp_panelize_peers_f32
+ * can read every rank's row block over NVLink with ordinary loads.  `alloc` returns the device pointer (0 on failure)
+ * and writes the 64-byte IPC handle to handle_out (host memory); `open` maps a peer's handle and returns the peer
+ * pointer valid in this process; `copy2d` publishes a [rows x cols] fp32 block into such a buffer (stream-ordered). */
+int64_t gnngp_exchange_alloc(size_t bytes, void *handle_out);
+int64_t gnngp_exchange_open(const void *handle);
+int gnngp_exchange_close(int64_t peer_ptr);
+int gnngp_exchange_free(int64_t ptr);
+int gnngp_copy2d_f32(const float *src, int64_t lds, int64_t rows, int64_t cols, int64_t dst_ptr, int64_t ldd,
+                     gnngp_stream_t stream);
+
 /* ---- K9: posterior solve for all nuggets by band reduction (csrc/bandfit.cu) ------------------------------------
  * Replaces `w, v = torch.linalg.eigh(Q[mb].T @ Q[mb])` and the per-nugget `v @ (temp / (w + eps*d))` of
  * src/predict.py:57-62.  gram: fp32 [m x m], LOWER triangle valid (gnngp_syrk_f32's output); rhs_t: fp32 [C x m] =
