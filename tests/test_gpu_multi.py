@@ -32,3 +32,27 @@ def test_sharded_nccl_run_matches_single_gpu_run():
         assert row["qqT_rel"] <= 1e-5, (name, row)
         assert row["fit_mid_rel"] <= 1e-3, (name, row)
         assert row["val_curve_maxdiff"] <= 2e-3 and row["test_curve_maxdiff"] <= 2e-3, (name, row)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs a second GPU")
+def test_model_on_a_non_current_device_matches_device_zero():
+    """every operator must run on the device of its tensors, whatever the current device is
+    (the reference honours ``--device`` because torch ops guard themselves, src/main.py:68)."""
+    import cases
+    from gnngp_b200.gnngp import GNNGP
+    case = cases.CASES["small-GCN-nys4-L2"]
+    data, masks, nugget = cases.build_inputs(case)
+    outs = []
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        torch.cuda.set_device(0)                                   # current device stays 0 for both models
+        model = GNNGP(data, device=dev, Nystrom=True)
+        model.mask["landmark"] = masks["landmark"].to(dev)
+        model.set_hyper_param(case["L"], case["sigma_b"], case["sigma_w"], method="GCN")
+        fit = model.predict(nugget.to(dev))
+        assert fit.device == dev and model.Q.device == dev
+        outs.append((model.Q.double().cpu(), fit.cpu(), {k: v.clone() for k, v in model.result.items()}))
+    qa, qb = outs[0][0][:300], outs[1][0][:300]
+    assert float((qa @ qa.T - qb @ qb.T).norm() / (qb @ qb.T).norm()) < 1e-5
+    assert float((outs[0][1][50] - outs[1][1][50]).norm() / outs[1][1][50].norm()) < 1e-3
+    for key in ("train", "val", "test"):
+        assert float((outs[0][2][key] - outs[1][2][key]).abs().max()) < 5e-3

@@ -168,3 +168,22 @@ def test_zz_write_parity_report():
                  for kk, vv in v.items()} for k, v in REPORT.items()}
     with open(os.path.join("gpurun_out", "parity_report.json"), "w") as fh:
         json.dump(clean, fh, indent=1, sort_keys=True)
+
+
+def test_csr_cache_follows_in_place_edits_of_the_adjacency():
+    """the cached CSR is keyed on the COO tensors' version counters, so an in-place edit of A's values
+    is picked up by the next kernel computation (the reference re-reads A on every product)."""
+    from gnngp_b200.gnngp import GNNGP
+    dev = torch.device("cuda:0")
+    case = cases.CASES["small-GCN-nys4-L2"]
+    data, masks, nugget = cases.build_inputs(case)
+    model = GNNGP(data, device=dev, Nystrom=True)
+    model.mask["landmark"] = masks["landmark"].to(dev)
+    model.set_hyper_param(2, 0.0, 1.0, method="GCN")
+    q1 = model.get_kernel().clone()
+    model.A._values().mul_(2.0)                                    # A <- 2 A in place
+    model.set_hyper_param(2, 0.0, 1.0, method="GCN")
+    q2 = model.get_kernel()
+    # first layer scales by 2; the ReLU expectation is 1-homogeneous in each argument, the second propagation doubles again
+    a, b = q1[:200].double(), q2[:200].double()
+    assert float(((b @ b.T) - 16.0 * (a @ a.T)).norm() / (16.0 * (a @ a.T)).norm()) < 1e-4
