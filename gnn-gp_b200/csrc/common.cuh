@@ -10,6 +10,7 @@ namespace gnngp {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+void count_tc_launch();      // launches of the tcgen05 contraction kernel (smoke() proves the fast path ran)
 
 inline cudaStream_t as_stream(gnngp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -527,6 +527,7 @@ static int gemm_nt_tc(const float *A, int64_t lda, const float *B, int64_t ldb, 
         kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, k_blocks, tiles_m, tiles_n, 1, tile_list, slots, epi);
     }
     GNNGP_LAUNCHED();
+    count_tc_launch();
     return GNNGP_OK;
 }
 

@@ -12,6 +12,7 @@ namespace gnngp {
 
 static thread_local char g_error[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<int64_t> g_tc_launches{0};
 std::atomic<int> g_gemm_engine{2};
 
 void set_error(const char *fmt, ...)
@@ -23,6 +24,7 @@ void set_error(const char *fmt, ...)
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count()
 {
@@ -80,6 +82,8 @@ int gnngp_set_gemm_engine(int engine)
 }
 
 int64_t gnngp_launch_count(void) { return gnngp::g_launches.load(); }
+
+int64_t gnngp_tc_launch_count(void) { return gnngp::g_tc_launches.load(); }
 
 
 // ---- peer exchange buffers (CUDA IPC), see include/gnngp_b200.h

@@ -139,6 +139,9 @@ class CudaOps(object):
     def launch_count(self) -> int:
         return int(self.lib.query("gnngp_launch_count"))
 
+    def tc_launch_count(self) -> int:
+        return int(self.lib.query("gnngp_tc_launch_count"))
+
     def set_gemm_engine(self, engine: int) -> int:
         return int(self.lib.query("gnngp_set_gemm_engine", int(engine)))
 
@@ -672,7 +675,7 @@ def _guarded(fn):
 
 for _name, _fn in list(vars(CudaOps).items()):
     if callable(_fn) and not _name.startswith("_") and not isinstance(_fn, (staticmethod, classmethod)) and _name not in (
-            "workspace", "release_workspace", "side_stream", "launch_count", "set_gemm_engine", "clear_cache"):
+            "workspace", "release_workspace", "side_stream", "launch_count", "tc_launch_count", "set_gemm_engine", "clear_cache"):
         setattr(CudaOps, _name, _guarded(_fn))
 del _name, _fn
 

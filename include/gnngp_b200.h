@@ -46,6 +46,8 @@ int gnngp_device_info(int *host_sm_count, int *host_cc_major, int *host_cc_minor
 int gnngp_set_gemm_engine(int engine);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gnngp_launch_count(void);
+/* Number of launches of the tcgen05 / TMEM / TMA contraction kernel since load. */
+int64_t gnngp_tc_launch_count(void);
 
 /* ---- adjacency: COO -> CSR ---------------------------------------------------------------
  * Replaces the implicit coalesce ATen runs on the sparse operand of every `A @ X`
