@@ -580,23 +580,39 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
                            int *__restrict__ info)
 {
     extern __shared__ double sm[];
-    double *win = sm;                                       // SLOTS x WIN: slot (j % SLOTS) holds column j: A[j + k][j], k = 0..BW
-    double *rwin = win + SLOTS * WIN;                       // SLOTS x RHS_MAX: right-hand-side rows / solution rows
-    double *lcol = rwin + SLOTS * RHS_LD;                  // WIN: the finished column of L
+    double *rwin = sm;                                      // SLOTS x RHS_LD: right-hand-side rows / solution rows, slot j % SLOTS
+    double *win = rwin + SLOTS * RHS_LD;                    // backward pass: factor-column and y rings (2 x CH x (WIN + RHS_MAX))
+    double *lcol = win + 2 * CH * (WIN + RHS_MAX);          // WIN: the finished column of L
     double *ycur = lcol + WIN;                              // RHS_MAX
+    double *colbuf = ycur + RHS_MAX;                        // WIN: the column being finished, published by its owners
     const int g = blockIdx.x, t = threadIdx.x;
-    const int lane = t & 31, warp = t >> 5;
     const double shift = shifts[g];
     double *L = Lg + (int64_t)g * m * WIN;
     double *sol = sol_t + (int64_t)g * nrhs * lds;
     int bad = 0;
 
-    auto prefetch_columns = [&](int64_t first, int count) {  // asynchronous: band columns + right-hand-side rows
-        for (int idx = t; idx < count * WIN; idx += SOLVE_THREADS) {
-            const int64_t j = first + idx / WIN;
-            const int k = idx % WIN;
-            if (j < m) cp_async8(&win[(int)(j % SLOTS) * WIN + k], Bd + j * WIN + k);
+    // The band window lives in REGISTERS: slot s (column j with j % SLOTS == s) is owned by 7 threads, 19 band offsets
+    // each.  A step then costs every thread two shared-memory reads per FMA-free... per owned entry (L[i], broadcast
+    // L[l]) instead of a read-modify-write of shared memory (13 k warp-instructions per column before, ~3 k now).
+    // A retired slot's owners load its next column (j + SLOTS) straight from global memory into their registers; the
+    // first use is SLOTS - WIN = 16 steps later, so the loads never stall a step.
+    const int own_slot = t / 7, sub = t - own_slot * 7;
+    const bool owner = own_slot < SLOTS;
+    const int o0 = sub * 19;
+    double a[19];
+    auto load_band = [&](int64_t col) {
+#pragma unroll
+        for (int q = 0; q < 19; ++q) {
+            const int o = o0 + q;
+            a[q] = (col < m && o <= BW) ? __ldg(Bd + col * WIN + o) : 0.0;
         }
+    };
+    if (owner) load_band(own_slot);
+    else {
+#pragma unroll
+        for (int q = 0; q < 19; ++q) a[q] = 0.0;
+    }
+    auto prefetch_rhs = [&](int64_t first, int count) {      // asynchronous: right-hand-side rows of `count` columns
         for (int idx = t; idx < count * RHS_MAX; idx += SOLVE_THREADS) {
             const int64_t j = first + idx / RHS_MAX;
             const int r = idx % RHS_MAX;
@@ -604,26 +620,31 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
         }
         cp_async_commit();
     };
-    prefetch_columns(0, WIN + CH);                          // columns 0 .. WIN + CH - 1
+    prefetch_rhs(0, WIN + CH);
     cp_async_wait_all();
     __syncthreads();
-    prefetch_columns(WIN + CH, CH);                         // in flight while the first chunk is factorised
+    prefetch_rhs(WIN + CH, CH);
 
     // ---- factorisation + forward substitution
     int slot = 0;                                            // j % SLOTS, kept incrementally (32-bit)
     for (int64_t j = 0; j < m; ++j, slot = (slot + 1 == SLOTS) ? 0 : slot + 1) {
         if (j > 0 && j % CH == 0) {
-            // columns up to j + WIN + CH - 1 are needed during this chunk: the group issued one chunk ago has them
-            cp_async_wait_all();
+            cp_async_wait_all();                             // rows up to j + WIN + CH - 1 are needed during this chunk
             __syncthreads();
-            prefetch_columns(j + WIN + CH, CH);              // their slots held columns j - CH .. j - 1 (finished)
+            prefetch_rhs(j + WIN + CH, CH);                  // their slots held rows j - CH .. j - 1 (finished)
         }
         const int kn = (int)min((int64_t)BW, m - 1 - j);
-        const double d = win[slot * WIN] + shift;
+        if (owner && own_slot == slot) {                     // publish column j
+#pragma unroll
+            for (int q = 0; q < 19; ++q)
+                if (o0 + q <= BW) colbuf[o0 + q] = a[q];
+        }
+        __syncthreads();
+        const double d = colbuf[0] + shift;
         if (!(d > 0.0)) bad = 1;
         const double inv = rsqrt(d);
         if (t <= kn) {
-            const double v = (t == 0) ? d * inv : win[slot * WIN + t] * inv;
+            const double v = (t == 0) ? d * inv : colbuf[t] * inv;
             lcol[t] = v;
             L[j * WIN + t] = v;
         } else if (t < WIN) {
@@ -633,15 +654,20 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
             ycur[t - 256] = y;
             sol[(int64_t)(t - 256) * lds + j] = y;            // y, overwritten by z in the backward pass
         }
+        if (owner && own_slot == slot) load_band(j + SLOTS);  // this slot's next column (used 16 steps from now)
         __syncthreads();
-        // trailing update of the window: A[j+i][j+l] -= L[i] L[l], 1 <= l <= i <= kn: warp w takes l = w+1, w+33, ...;
-        // its lanes walk i = l, l+1, ... (contiguous offsets i - l in the slot of column j + l)
-        for (int l = warp + 1; l <= kn; l += SOLVE_THREADS / 32) {
-            int sl = slot + l;
-            if (sl >= SLOTS) sl -= SLOTS;
-            double *col = win + sl * WIN;
-            const double ll = lcol[l];
-            for (int i = l + lane; i <= kn; i += 32) col[i - l] = fma(-lcol[i], ll, col[i - l]);
+        // trailing update: A[j+i][j+l] -= L[i] L[l] for the owned entries of column j + l (offset o = i - l)
+        if (owner) {
+            int l = own_slot - slot;
+            if (l < 0) l += SLOTS;
+            if (l >= 1 && l <= kn) {
+                const double ll = lcol[l];
+#pragma unroll
+                for (int q = 0; q < 19; ++q) {
+                    const int i = o0 + q + l;
+                    if (o0 + q <= BW && i <= kn) a[q] = fma(-lcol[i], ll, a[q]);
+                }
+            }
         }
         // right-hand sides: row j+i -= L[i] y      (8 threads per row i, 6 columns each)
         {
@@ -654,7 +680,6 @@ band_cholesky_solve_kernel(const double *__restrict__ Bd, int64_t m, const doubl
                 for (int r = t & 7; r < nrhs; r += 8) row[r] = fma(-li, ycur[r], row[r]);
             }
         }
-        __syncthreads();
     }
     cp_async_wait_all();
     if (bad && t == 0) atomicAdd(info, 1);
@@ -910,7 +935,7 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
 
     // ---- one CTA per shift: banded Cholesky + substitutions
     {
-        const size_t smem = (size_t)(SLOTS * WIN + SLOTS * RHS_LD + WIN + RHS_MAX) * sizeof(double);
+        const size_t smem = (size_t)(SLOTS * RHS_LD + 2 * CH * (WIN + RHS_MAX) + WIN + RHS_MAX + WIN) * sizeof(double);
         GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(band_cholesky_solve_kernel), (int)smem));
         band_cholesky_solve_kernel<<<(unsigned)G, SOLVE_THREADS, smem, st>>>(Bd, m, shifts, rhs, m, (int)C, Lg, sol, m, info);
         GNNGP_LAUNCHED();
