@@ -1,0 +1,223 @@
+"""The Nyström root ``_sqrt_Nystrom`` (reference ``src/compute.py:6-17``) WITHOUT a full eigendecomposition.
+
+The reference computes ``D, V = eigh(M)`` of the landmark block ``M = K[mask]`` and returns
+``Q[mask] = V sqrt(D+)``, ``Q[~mask] = K[~mask] V diag(sqrt(D+) / max(D, tau))`` with ``tau = 1e-4 D_max``.  Every
+consumer of ``Q`` sees only ``Q Qᵀ`` (the next layer's Gram, the fit's ``Q_bᵀ Q_b``), so any ``Q R`` with an orthogonal
+``R`` is the same factor.  Write ``f(lam) = lam / max(lam, tau)^2`` (so that ``Q[~mask] Q[~mask]ᵀ = K f(M) Kᵀ``); below
+the clamp ``f`` is LINEAR, ``f(lam) = lam / tau^2``, hence
+
+    f(M) = M / tau^2 + V_t diag(1/lam - lam/tau^2) V_tᵀ            (V_t, lam: the eigenpairs ABOVE tau only)
+
+and with the Cholesky factor ``M = L Lᵀ`` the matrix
+
+    S = L / tau + V_t diag(1/lam - 1/tau) V_tᵀ L                    satisfies  S Sᵀ = f(M)  and  M S = ... = L-consistent:
+
+``Q[mask] = L`` and ``Q[~mask] = K[~mask] S`` is the reference's factor times one orthogonal matrix (``R = S_ref⁻¹ S``).
+On the benchmark graph 647 of 15 404 eigenvalues lie above the clamp: instead of a 15 404² eigendecomposition
+(cuSOLVER fp64: 2.28 s on B200, bound by the one-stage tridiagonalisation) the route needs
+
+  * one dense fp64 Cholesky factorisation (n³/3 flops, blocked, own DMMA GEMM),
+  * the eigenpairs above ``tau`` from a block Lanczos process with full re-orthogonalisation (block 128, Krylov
+    dimension ~0.11 n; every product ``M V_j`` is one fp64 GEMM) and a Rayleigh–Ritz step on the small projected matrix,
+  * three skinny GEMMs that assemble ``Sᵀ``.
+
+Everything is fp64: ``S`` cancels ``L / tau`` against the top of the spectrum (1/tau against 1/lam_max = 1e-4 / tau), which
+needs the top Ritz vectors to ~1e-10; a Ritz pair (theta, y) is accepted when ``|M y - theta y| <= tol * tau * theta_max /
+theta`` (the residual bound under which the error of ``Q Qᵀ`` stays below ~1e-8, measured against the full
+eigendecomposition on the benchmark's landmark block: 1.7e-10 at Krylov dimension 1 664).  When the Cholesky factorisation
+meets a non-positive pivot (an indefinite or rank-deficient block, which the reference's clamp tolerates) or the Ritz
+pairs above the clamp do not converge within the dimension budget (a spectrum with most of its eigenvalues above the
+clamp, e.g. fraction 50), the caller takes the reference's eigen route instead.
+
+This module is host logic only; the operators (``sym_f64``, ``dgemm``, ``potrf_f64``, ``potrf_inv_block``, ...) are
+CUDA kernels behind the C ABI (``csrc/dense64.cu``); the CPU suite drives this logic through a test-only stand-in.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+
+DEFAULT_BLOCK = 128              # Lanczos block = the Cholesky panel width of csrc/dense64.cu
+CLAMP = 1e-4                     # src/compute.py:13
+RESIDUAL_TOL = 1e-7              # see the module docstring
+# Krylov dimensions (fractions of n) at which a Rayleigh-Ritz check is made; past the last one the route gives up
+CHECKPOINTS = (0.11, 0.16, 0.23)
+
+
+def wanted(n: int, ops) -> bool:
+    """Route policy: ``GNNGP_ROOT_SOLVER`` = eigh | krylov | auto (default).  auto takes the Krylov route for blocks of
+    at least 4 096 landmarks (below that cuSOLVER's eigh costs less than the Cholesky factorisation plus the Lanczos
+    steps: 54 ms at n = 3 052) when the operator set has the fp64 kernels."""
+    mode = os.environ.get("GNNGP_ROOT_SOLVER", "auto")
+    if mode == "eigh" or not hasattr(ops, "dgemm"):
+        return False
+    if mode == "krylov":
+        return n >= 2 * DEFAULT_BLOCK
+    return n >= 4096
+
+
+def _checkpoint_blocks(n: int, block: int):
+    out = []
+    for frac in CHECKPOINTS:
+        blocks = int(math.ceil(frac * n / block))
+        blocks = max(2, min(blocks, n // block - 1))
+        if blocks * block < n and (not out or blocks > out[-1]):
+            out.append(blocks)
+    return out
+
+
+class _Phases(object):
+    """Per-phase wall times of one call (device-synchronised), only when ``stats["time"]`` is set (tools/root_probe.py)."""
+
+    def __init__(self, stats, dev):
+        self.on = bool(stats is not None and stats.get("time")) and dev.type == "cuda"
+        self.stats, self.dev, self.t0 = stats, dev, None
+        if self.on:
+            import time
+            self.clock = time.perf_counter
+            torch.cuda.synchronize(dev)
+            self.t0 = self.clock()
+            stats["phase_ms"] = {}
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize(self.dev)
+            now = self.clock()
+            self.stats["phase_ms"][name] = self.stats["phase_ms"].get(name, 0.0) + 1e3 * (now - self.t0)
+            self.t0 = now
+
+
+def _orthonormalise(ops, w: torch.Tensor, out: torch.Tensor, info: torch.Tensor, gram: torch.Tensor, tmp: torch.Tensor) -> None:
+    """``out = w R⁻¹`` with orthonormal columns by two rounds of Cholesky-QR (``wᵀw = R_1ᵀR_1``, ...): three GEMMs and
+    one 128 x 128 factorisation + triangular inverse per round; a breakdown (rank-deficient block) lands in ``info``."""
+    ops.dgemm(w.T, w, out=gram)
+    linv = ops.potrf_inv_block(gram, info)
+    ops.dgemm(w, linv.T, out=tmp)
+    ops.dgemm(tmp.T, tmp, out=gram)
+    linv = ops.potrf_inv_block(gram, info)
+    ops.dgemm(tmp, linv.T, out=out)
+
+
+def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
+                 block: Optional[int] = None) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """(``Sᵀ`` as the fp32 B operand of ``E @ S`` — the role of ``(V D~)ᵀ`` in ``Pipeline._root_factors`` — and the
+    fp32 landmark rows ``L``), or ``None`` when the route does not apply to this block (the caller then runs ``eigh``).
+    ``kmm``: fp32 [n x n] landmark block, lower triangle read.  ``block`` (<= 128) is the Lanczos block size."""
+    n = kmm.shape[0]
+    dev = kmm.device
+    BLOCK = int(block if block is not None else os.environ.get("GNNGP_ROOT_BLOCK", DEFAULT_BLOCK))   # <= 128 (tests: 32)
+    checkpoints = _checkpoint_blocks(n, BLOCK)
+    if not checkpoints:
+        return None
+    f64 = torch.float64
+    phases = _Phases(stats, dev)
+    m64 = ops.sym_f64(kmm)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    # ---- Cholesky factor (a copy: the Lanczos products need M itself)
+    chol = m64.clone()
+    ops.potrf_f64(chol, info)
+    phases.mark("cholesky")
+
+    # ---- block Lanczos with full re-orthogonalisation
+    dim_max = (checkpoints[-1] + 1) * BLOCK
+    basis = torch.empty((n, dim_max), dtype=f64, device=dev)        # K = [V_0 V_1 ...]
+    mbasis = torch.empty((n, dim_max), dtype=f64, device=dev)       # M K
+    work = torch.empty((n, BLOCK), dtype=f64, device=dev)
+    tmp = torch.empty((n, BLOCK), dtype=f64, device=dev)
+    gram = torch.empty((BLOCK, BLOCK), dtype=f64, device=dev)
+    coef = torch.empty((dim_max, BLOCK), dtype=f64, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20240229)
+    work.copy_(torch.randn((n, BLOCK), dtype=f64, device=dev, generator=gen))
+    _orthonormalise(ops, work, basis[:, :BLOCK], info, gram, tmp)
+
+    result = None
+    blocks_done = 0                                                  # blocks j with M V_j stored
+    for target in checkpoints:
+        while blocks_done < target:
+            j = blocks_done
+            vj = basis[:, j * BLOCK:(j + 1) * BLOCK]
+            mv = mbasis[:, j * BLOCK:(j + 1) * BLOCK]
+            ops.dgemm(m64, vj, out=mv)
+            blocks_done += 1
+            if blocks_done == target and target == checkpoints[-1]:
+                break                                                # the last block is only needed for the projection
+            have = basis[:, :(j + 1) * BLOCK]
+            work.copy_(mv)
+            for _ in range(2):                                       # classical Gram-Schmidt, twice
+                c = coef[:(j + 1) * BLOCK]
+                ops.dgemm(have.T, work, out=c)
+                ops.dgemm(have, c, out=work, alpha=-1.0, beta=1.0)
+            _orthonormalise(ops, work, basis[:, (j + 1) * BLOCK:(j + 2) * BLOCK], info, gram, tmp)
+        dim = blocks_done * BLOCK
+        phases.mark("lanczos")
+        got = _rayleigh_ritz(ops, chol, basis[:, :dim], mbasis[:, :dim], info, stats, BLOCK, phases)
+        if isinstance(got, str):                                     # "breakdown"
+            break
+        if got is not None:
+            result = got
+            break
+        # the basis needs block `blocks_done` next: it exists unless the last product was the final one
+        if target == checkpoints[-1]:
+            break
+    if stats is not None:
+        stats["krylov_dim"] = blocks_done * BLOCK
+        stats["converged"] = result is not None
+    return result
+
+
+def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases):
+    """Project, solve the small eigenproblem, test the Ritz pairs above the clamp, assemble ``Sᵀ``.  Returns the pair of
+    factors, ``None`` (not converged at this dimension) or ``"breakdown"`` (non-positive pivot somewhere)."""
+    n, dim = basis.shape
+    dev = basis.device
+    f64 = torch.float64
+    h = torch.empty((dim, dim), dtype=f64, device=dev)
+    ops.dgemm(basis.T, mbasis, out=h)
+    # the one host synchronisation of the route: pivot flag + Ritz values
+    if int(info.item()) != 0:
+        return "breakdown"
+    theta, y = ops.eigh_small_f64(h)                                 # ascending
+    phases.mark("projected_eigh")
+    theta_host = theta.cpu()
+    top = float(theta_host[-1])
+    if not (top > 0.0) or not bool(torch.isfinite(theta_host).all()):
+        return "breakdown"
+    tau = CLAMP * top
+    k = int((theta_host > tau).sum())
+    k_check = int((theta_host > 0.9 * tau).sum())                    # Ritz values just below the clamp are tested too
+    if stats is not None:
+        stats.setdefault("ritz_above_clamp", []).append(k)
+    if k_check + block > dim:                                        # the Krylov space has not reached past the clamp yet
+        return None
+    sel = theta_host[dim - k_check:]
+    y_sel = y[:, dim - k_check:]
+    ritz = torch.empty((n, k_check), dtype=f64, device=dev)
+    resid = torch.empty((n, k_check), dtype=f64, device=dev)
+    ops.dgemm(basis, y_sel, out=ritz)
+    ops.dgemm(mbasis, y_sel, out=resid)
+    theta_dev = sel.to(dev)
+    rnorm = torch.sqrt(ops.residual_sumsq(resid, ritz, theta_dev)).cpu()
+    allowed = RESIDUAL_TOL * tau * top / sel
+    allowed = torch.where(sel > tau, allowed, 100.0 * allowed)
+    worst = float((rnorm / allowed).max()) if k_check else 0.0
+    if stats is not None:
+        stats.setdefault("residual_over_allowed", []).append(worst)
+    phases.mark("ritz_vectors")
+    if not worst <= 1.0:
+        return None
+    # ---- S^T = L^T / tau + (L^T V_t) diag(1/theta - 1/tau) V_t^T          (V_t: the k Ritz vectors above the clamp)
+    vt = ritz[:, k_check - k:]
+    weights = (1.0 / sel[k_check - k:] - 1.0 / tau).to(dev)
+    st = ops.transpose_scale_f64(chol, 1.0 / tau)
+    if k > 0:
+        p = resid[:, :k]                                             # [n x k] scratch (the residuals are spent)
+        ops.dgemm(chol.T, vt, out=p)
+        vw = ops.scale_cols_f64(vt, weights)
+        ops.dgemm(p, vw.T, out=st, beta=1.0)
+    out = ops.to_f32(st), ops.to_f32(chol)
+    phases.mark("assemble")
+    return out

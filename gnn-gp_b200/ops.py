@@ -518,6 +518,98 @@ class CudaOps(object):
                       float(a), float(b), float(c), self._stream())
         return out
 
+    # ------------------------------------------------------------------ fp64 dense operators (Krylov Nystrom root)
+    @staticmethod
+    def _f64_view(t: torch.Tensor, name: str) -> torch.Tensor:
+        if not t.is_cuda or t.dtype != torch.float64 or t.dim() != 2:
+            raise RuntimeError("gnngp_b200: %s must be a 2-D CUDA float64 tensor (got %s %s on %s)"
+                               % (name, tuple(t.shape), t.dtype, t.device))
+        return t
+
+    def sym_f64(self, kmm: torch.Tensor) -> torch.Tensor:
+        """Full symmetric fp64 copy of the LOWER triangle of an fp32 block."""
+        kmm, ldk = self._mat(kmm, "kmm")
+        n = kmm.shape[0]
+        if kmm.shape[1] != n:
+            raise RuntimeError("sym_f64: square block expected")
+        out = torch.empty((n, n), dtype=torch.float64, device=kmm.device)
+        self.lib.call("gnngp_sym_f64_from_f32", kmm.data_ptr(), ldk, n, out.data_ptr(), n, self._stream())
+        return out
+
+    def dgemm(self, A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, alpha: float = 1.0, beta: float = 0.0,
+              lower: bool = False) -> torch.Tensor:
+        """``out = alpha A @ B + beta out`` in fp64 on the DMMA path; ``A`` / ``B`` may be transposed or column-sliced
+        views (one unit stride each), ``out`` a row-major view.  ``lower``: only tiles touching the lower triangle."""
+        self._f64_view(A, "A"), self._f64_view(B, "B"), self._f64_view(out, "out")
+        m, k = A.shape
+        k2, n = B.shape
+        if k2 != k or tuple(out.shape) != (m, n) or (n > 1 and out.stride(1) != 1):
+            raise RuntimeError("dgemm: shapes %s @ %s -> %s" % (tuple(A.shape), tuple(B.shape), tuple(out.shape)))
+        self.lib.call("gnngp_dgemm_f64", m, n, k, A.data_ptr(), A.stride(0), A.stride(1), B.data_ptr(), B.stride(0),
+                      B.stride(1), float(alpha), float(beta), out.data_ptr(), out.stride(0) if m > 1 else max(n, out.stride(0)),
+                      1 if lower else 0, self._stream())
+        return out
+
+    def potrf_f64(self, A: torch.Tensor, info: torch.Tensor) -> torch.Tensor:
+        """In-place lower Cholesky factor of a symmetric fp64 matrix (strict upper triangle zeroed); ``info`` (device
+        int32) counts blocks with a non-positive pivot.  No host sync."""
+        self._f64_view(A, "A")
+        n = A.shape[0]
+        if A.shape[1] != n or A.stride(1) != 1:
+            raise RuntimeError("potrf_f64: square row-major matrix expected")
+        need = self.lib.query("gnngp_potrf_f64_workspace_bytes", n)
+        ws = self.workspace(need + 256, A.device, "potrf")
+        wptr = (ws.data_ptr() + 255) // 256 * 256
+        self.lib.call("gnngp_potrf_f64", A.data_ptr(), A.stride(0), n, info.data_ptr(), wptr, need, self._stream())
+        return A
+
+    def potrf_inv_block(self, G: torch.Tensor, info: torch.Tensor) -> torch.Tensor:
+        """One block of at most 128 rows: Cholesky factor in place (lower triangle) and the returned ``L⁻¹``."""
+        self._f64_view(G, "G")
+        nb = G.shape[0]
+        linv = torch.empty((nb, nb), dtype=torch.float64, device=G.device)
+        self.lib.call("gnngp_potrf_inv_block_f64", G.data_ptr(), G.stride(0), nb, linv.data_ptr(), nb, info.data_ptr(),
+                      self._stream())
+        return linv
+
+    def eigh_small_f64(self, H: torch.Tensor):
+        """Rayleigh-Ritz step of the Krylov root: eigendecomposition of the SMALL projected matrix (dimension ~0.11 n;
+        cuSOLVER through torch, 1/200 of the flops of the eigendecomposition it replaces)."""
+        return torch.linalg.eigh(H)
+
+    def residual_sumsq(self, R: torch.Tensor, V: torch.Tensor, theta: torch.Tensor) -> torch.Tensor:
+        self._f64_view(R, "R"), self._f64_view(V, "V")
+        n, k = R.shape
+        theta = theta.contiguous()
+        out = torch.empty(k, dtype=torch.float64, device=R.device)
+        self.lib.call("gnngp_residual_sumsq_f64", R.data_ptr(), R.stride(0), V.data_ptr(), V.stride(0), theta.data_ptr(), n, k,
+                      out.data_ptr(), self._stream())
+        return out
+
+    def transpose_scale_f64(self, A: torch.Tensor, alpha: float) -> torch.Tensor:
+        self._f64_view(A, "A")
+        rows, cols = A.shape
+        out = torch.empty((cols, rows), dtype=torch.float64, device=A.device)
+        self.lib.call("gnngp_transpose_scale_f64", A.data_ptr(), A.stride(0), rows, cols, float(alpha), out.data_ptr(), rows,
+                      self._stream())
+        return out
+
+    def scale_cols_f64(self, V: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+        self._f64_view(V, "V")
+        rows, cols = V.shape
+        d = d.contiguous()
+        out = torch.empty((rows, cols), dtype=torch.float64, device=V.device)
+        self.lib.call("gnngp_scale_cols_f64", V.data_ptr(), V.stride(0), rows, cols, d.data_ptr(), out.data_ptr(), cols,
+                      self._stream())
+        return out
+
+    def to_f32(self, A: torch.Tensor) -> torch.Tensor:
+        self._f64_view(A, "A")
+        rows, cols = A.shape
+        out = self.empty(rows, cols, A.device)
+        self.lib.call("gnngp_f64_to_f32", A.data_ptr(), A.stride(0), rows, cols, out.data_ptr(), self._ld(out), self._stream())
+        return out
+
     # ------------------------------------------------------------------ Nystrom root pieces
     # dtype the eigensolver runs in.  Measured on B200 (profiles/r1/accuracy_probe.json): cuSOLVER's fp32
     # syevd/syevj through torch loses ~50x accuracy against LAPACK's ssyevd on the clamped Nystrom root

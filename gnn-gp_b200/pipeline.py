@@ -19,6 +19,8 @@ from typing import Dict, Optional
 
 import torch
 
+from . import krylov_root
+
 
 class LocalComm(object):
     """World of one: the single-GPU drop-in path."""
@@ -95,8 +97,19 @@ class Pipeline(object):
         return full
 
     def _root_factors(self, kmm: torch.Tensor):
-        """eigh of the landmark block and the two column scalings of src/compute.py:11-13."""
+        """The two factors of the Nystrom root (src/compute.py:11-16): the B operand of ``E @ S`` and the landmark rows.
+        Large blocks take the Krylov route (``krylov_root``: Cholesky factor + the eigenpairs above the clamp only);
+        otherwise, or when that route reports an indefinite block or no convergence, the reference's eigen route:
+        eigh of the landmark block and the two column scalings."""
         ops = self.ops
+        if krylov_root.wanted(kmm.shape[0], ops):
+            stats = {}
+            got = krylov_root.root_factors(ops, kmm, stats)
+            self.last_root_stats = stats
+            if got is not None:
+                self.last_root_solver = ops.last_root_solver = "krylov"
+                return got
+        self.last_root_solver = ops.last_root_solver = "eigh"
         evals, evecs = ops.eigh(kmm)
         root, inv = ops.nystrom_spectrum(evals)
         w_t = ops.scale_cols(evecs, inv, transpose=True)      # (V * D^-1/2~)^T, the B operand of E @ (V D~)

@@ -221,6 +221,38 @@ int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, const float *r
                        const double *shifts, int64_t G, float *coeff_t, int64_t ldo, int32_t *info, void *workspace,
                        size_t workspace_bytes, gnngp_stream_t stream);
 
+/* ---- K10: fp64 dense operators of the Krylov Nystrom root (csrc/dense64.cu, gnn-gp_b200/krylov_root.py) ---------
+ * Together they replace `D, V = torch.linalg.eigh(K[mask])` of src/compute.py:11 for large landmark blocks: the root
+ * only needs the Cholesky factor of the block and the eigenpairs ABOVE the clamp D[-1]*1e-4 (src/compute.py:13), which
+ * a block Lanczos process made of these calls delivers (host logic in krylov_root.py).  All matrices fp64 row-major.
+ *   sym_f64_from_f32     a[n x n] = symmetric copy of the LOWER triangle of the fp32 block g
+ *   dgemm_f64            C[m x n] = alpha A B + beta C on the fp64 tensor path; A(i,p) = a[i*a_rs + p*a_cs],
+ *                        B(p,j) = b[p*b_rs + j*b_cs] (one unit stride per operand: plain or transposed views);
+ *                        lower != 0 computes only the 128 x 64 tiles that touch the lower triangle (symmetric updates)
+ *   potrf_f64            in-place blocked Cholesky factorisation a = L L^T (lower triangle read, strict upper triangle
+ *                        zeroed on return); info (device int32) is incremented once per block that met a non-positive pivot
+ *   potrf_inv_block_f64  one block of nb <= 128 rows: L in place and, when linv != NULL, L^-1 (full nb x nb, zeros above)
+ *   residual_sumsq_f64   out[j] = sum_i (r[i][j] - theta[j] v[i][j])^2  (Ritz residuals |M y - theta y|^2)
+ *   transpose_scale_f64  out[j][i] = alpha a[i][j];  scale_cols_f64  out[i][j] = v[i][j] d[j];  f64_to_f32  dst = (float)src
+ * No host synchronisation in any of them. */
+int gnngp_sym_f64_from_f32(const float *g, int64_t ldg, int64_t n, double *a, int64_t lda, gnngp_stream_t stream);
+int gnngp_dgemm_f64(int64_t m, int64_t n, int64_t k, const double *a, int64_t a_rs, int64_t a_cs, const double *b,
+                    int64_t b_rs, int64_t b_cs, double alpha, double beta, double *c, int64_t ldc, int lower,
+                    gnngp_stream_t stream);
+size_t gnngp_potrf_f64_workspace_bytes(int64_t n);
+int gnngp_potrf_f64(double *a, int64_t lda, int64_t n, int32_t *info, void *workspace, size_t workspace_bytes,
+                    gnngp_stream_t stream);
+int gnngp_potrf_inv_block_f64(double *a, int64_t lda, int64_t nb, double *linv, int64_t ldi, int32_t *info,
+                              gnngp_stream_t stream);
+int gnngp_residual_sumsq_f64(const double *r, int64_t ldr, const double *v, int64_t ldv, const double *theta, int64_t n,
+                             int64_t k, double *out, gnngp_stream_t stream);
+int gnngp_transpose_scale_f64(const double *a, int64_t lda, int64_t rows, int64_t cols, double alpha, double *out,
+                              int64_t ldo, gnngp_stream_t stream);
+int gnngp_scale_cols_f64(const double *v, int64_t ldv, int64_t rows, int64_t cols, const double *d, double *out,
+                         int64_t ldo, gnngp_stream_t stream);
+int gnngp_f64_to_f32(const double *src, int64_t lds, int64_t rows, int64_t cols, float *dst, int64_t ldd,
+                     gnngp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,6 +131,51 @@ class StubOps(object):
     def eigh(self, M):
         return torch.linalg.eigh(M.contiguous())
 
+    # ---- fp64 dense operators of the Krylov Nystrom root (csrc/dense64.cu)
+    def sym_f64(self, kmm):
+        low = torch.tril(kmm).double()
+        return low + torch.tril(low, -1).T
+
+    def dgemm(self, A, B, out, alpha=1.0, beta=0.0, lower=False):
+        res = alpha * (A @ B)
+        if beta != 0.0:
+            res = res + beta * out
+        if lower:
+            res = torch.where(torch.ones_like(res, dtype=torch.bool).tril(), res, out)
+        out.copy_(res)
+        return out
+
+    def potrf_f64(self, A, info):
+        factor, bad = torch.linalg.cholesky_ex(A)
+        info += (bad != 0).to(torch.int32)
+        A.copy_(torch.tril(factor))
+        return A
+
+    def potrf_inv_block(self, G, info):
+        factor, bad = torch.linalg.cholesky_ex(G)
+        info += (bad != 0).to(torch.int32)
+        G.copy_(torch.tril(factor))
+        if int(bad) != 0:
+            return torch.eye(G.shape[0], dtype=G.dtype)
+        return torch.linalg.solve_triangular(G, torch.eye(G.shape[0], dtype=G.dtype), upper=False)
+
+    def eigh_small_f64(self, H):
+        return torch.linalg.eigh(H)
+
+    def residual_sumsq(self, R, V, theta):
+        return ((R - V * theta.view(1, -1)) ** 2).sum(0)
+
+    def transpose_scale_f64(self, A, alpha):
+        return (alpha * A.T).contiguous()
+
+    def scale_cols_f64(self, V, d):
+        return V * d.view(1, -1)
+
+    def to_f32(self, A):
+        out = self.empty(A.shape[0], A.shape[1])
+        out.copy_(A)
+        return out
+
     def shifted_solves(self, gram, rhs_t, shifts):
         m, c = gram.shape[0], rhs_t.shape[0]
         sym = torch.tril(gram).double()
