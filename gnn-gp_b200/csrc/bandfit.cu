@@ -609,6 +609,64 @@ static int apply_reflector(double *X, int64_t ldx, int64_t n_vec, int64_t r0, in
     return dgemm(n_vec, s, BW, View{P2, BW, 1}, View{V, 1, BW}, 0, kNoView, kNoView, -1.0, 1.0, X + r0, ldx, 1, st);
 }
 
+// Householder QR of one s x BW panel: the cluster kernel for short panels, the cooperative grid otherwise.
+struct PanelScratch { double *gbuf, *rowk; unsigned int *counter; bool cluster_ok; int sms; };
+
+static int panel_qr_setup(PanelScratch &ps)
+{
+    int coop = 0, dev = 0;
+    GNNGP_CUDA(cudaGetDevice(&dev));
+    GNNGP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GNNGP_REQUIRE(coop, "band_fit: the device does not support cooperative launches");
+    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_kernel), 208 * LDP * (int)sizeof(double)));
+    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_cluster_kernel), 208 * LDP * (int)sizeof(double)));
+    ps.cluster_ok = cudaFuncSetAttribute(sbr_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    ps.sms = sm_count();
+    return GNNGP_OK;
+}
+
+static int panel_qr(const double *Ap, int64_t lda, int64_t s, double *Vp, double *R, double *Tq, PanelScratch &ps, cudaStream_t st)
+{
+    int64_t lda_arg = lda, s_arg = s;
+    if (s <= 15 * 208 && ps.cluster_ok) {
+        // one thread-block cluster: up to 15 slab CTAs + the CTA that builds T
+        int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, 15), 8));
+        const int n_cta = (int)ceil_div(s, rows_per) + 1;
+        const size_t smem = (size_t)rows_per * LDP * sizeof(double);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_cta);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = n_cta;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t err = cudaLaunchKernelEx(&cfg, sbr_panel_cluster_kernel, Ap, lda_arg, s_arg, rows_per, Vp, R, Tq);
+        if (err == cudaSuccess) {
+            count_launch();
+            return GNNGP_OK;
+        }
+        (void)cudaGetLastError();                           // e.g. the cluster does not fit this device: use the grid version
+        ps.cluster_ok = false;
+    }
+    // cooperative grid.  rows per CTA: at least BW (row k of every step lives in CTA 0), at most what fits shared memory
+    int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, ps.sms - 1), 8));   // one CTA of the grid builds T
+    GNNGP_REQUIRE(rows_per <= 208, "band_fit: %lld rows are too many for the shared-memory panel (max ~30 000)", (long long)s);
+    const int n_cta = (int)ceil_div(s, rows_per) + 1;
+    const size_t smem = (size_t)rows_per * LDP * sizeof(double);
+    GNNGP_CUDA(cudaMemsetAsync(ps.counter, 0, sizeof(unsigned int), st));
+    int rows_arg = rows_per;
+    void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&Tq,
+                    (void *)&ps.gbuf, (void *)&ps.rowk, (void *)&ps.counter};
+    GNNGP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(sbr_panel_kernel), dim3(n_cta), dim3(256), args, smem, st));
+    count_launch();
+    return GNNGP_OK;
+}
+
 }  // namespace bandfit
 }  // namespace gnngp
 
@@ -663,59 +721,14 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     GNNGP_LAUNCHED();
 
     // ---- band reduction, one panel at a time; the right-hand sides are transformed along the way (Q_p^T)
-    int coop = 0, dev = 0;
-    GNNGP_CUDA(cudaGetDevice(&dev));
-    GNNGP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    GNNGP_REQUIRE(coop, "band_fit: the device does not support cooperative launches");
+    PanelScratch ps{gbuf, rowk, counter, false, sms};
+    if ((rc = panel_qr_setup(ps)) != GNNGP_OK) return rc;
     double *Vp = Vall;
-    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_kernel), 208 * LDP * (int)sizeof(double)));
-    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(sbr_panel_cluster_kernel), 208 * LDP * (int)sizeof(double)));
-    bool cluster_ok = cudaFuncSetAttribute(sbr_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     for (int64_t q = 0; q < p.panels; ++q) {
         const int64_t j0 = q * BW, r0 = j0 + BW, s = m - r0;
         const double *Ap = A + r0 * lda + j0;
         double *Tq = Tall + q * BW * BW;
-        int64_t lda_arg = lda, s_arg = s;
-        bool done = false;
-        if (s <= 15 * 208 && cluster_ok) {
-            // one thread-block cluster: up to 15 slab CTAs + the CTA that builds T
-            int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, 15), 8));
-            const int n_cta = (int)ceil_div(s, rows_per) + 1;
-            const size_t smem = (size_t)rows_per * LDP * sizeof(double);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(n_cta);
-            cfg.blockDim = dim3(256);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = n_cta;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            const cudaError_t err = cudaLaunchKernelEx(&cfg, sbr_panel_cluster_kernel, Ap, lda_arg, s_arg, rows_per, Vp, R, Tq);
-            if (err == cudaSuccess) {
-                count_launch();
-                done = true;
-            } else {
-                (void)cudaGetLastError();                   // e.g. the cluster does not fit this device: use the grid version
-                cluster_ok = false;
-            }
-        }
-        if (!done) {
-            // cooperative grid.  rows per CTA: at least BW (row k of every step lives in CTA 0), at most what fits shared memory
-            int rows_per = (int)std::max<int64_t>(BW, round_up(ceil_div(s, sms - 1), 8));   // one CTA of the grid builds T
-            GNNGP_REQUIRE(rows_per <= 208, "band_fit: m = %lld is too large for the shared-memory panel (max ~30 000)", (long long)m);
-            const int n_cta = (int)ceil_div(s, rows_per) + 1;
-            const size_t smem = (size_t)rows_per * LDP * sizeof(double);
-            GNNGP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-            int rows_arg = rows_per;
-            void *args[] = {(void *)&Ap, (void *)&lda_arg, (void *)&s_arg, (void *)&rows_arg, (void *)&Vp, (void *)&R, (void *)&Tq,
-                            (void *)&gbuf, (void *)&rowk, (void *)&counter};
-            GNNGP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(sbr_panel_kernel), dim3(n_cta), dim3(256), args, smem, st));
-            count_launch();
-        }
+        if ((rc = panel_qr(Ap, lda, s, Vp, R, Tq, ps, st)) != GNNGP_OK) return rc;
         band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
         GNNGP_LAUNCHED();
         double *A22 = A + r0 * lda + r0;
@@ -765,5 +778,62 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     }
     to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(G * C * m, 256), (int64_t)sms * 16), 256, 0, st>>>(sol, m, G * C, m, coeff_t, ldo);
     GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X <- X Q_H, where Q_H is the orthogonal factor of the Householder QR of the tall block Z (n x kp, kp a multiple of
+// 128; Z is overwritten).  The first columns of Q_H are (up to sign) the orthonormalised columns of Z, the others an
+// orthonormal basis of the complement — the Krylov Nystrom root uses it to rotate the Cholesky factor into a basis
+// whose leading columns are the Ritz directions above the clamp (krylov_root.py).  Panel QR by the band-reduction
+// kernels above, block reflectors applied in GEMM form.
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t gnngp_qr_rotate_workspace_bytes(int64_t rows, int64_t n, int64_t kp)
+{
+    if (rows <= 0 || n <= 0 || kp <= 0) return 256;
+    return (size_t)n * BW * 8 + 3 * (size_t)BW * BW * 8 + 2 * (size_t)rows * BW * 8 + 2 * (size_t)BW * kp * 8 + 6 * BW * 8 + 4096;
+}
+
+extern "C" int gnngp_qr_rotate_f64(double *x, int64_t ldx, int64_t rows, double *z, int64_t ldz, int64_t n, int64_t kp,
+                                   void *workspace, size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(x && z && rows > 0 && n > 0 && kp > 0 && kp % BW == 0 && kp <= n && ldx >= n && ldz >= kp,
+                  "qr_rotate: Z must be [n x kp] with kp a multiple of %d and kp <= n", BW);
+    GNNGP_REQUIRE(workspace && aligned(workspace, 256) && workspace_bytes >= gnngp_qr_rotate_workspace_bytes(rows, n, kp),
+                  "qr_rotate: workspace must be 256-byte aligned and hold gnngp_qr_rotate_workspace_bytes(rows, n, kp)");
+    cudaStream_t st = as_stream(stream);
+    char *base = reinterpret_cast<char *>(workspace);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *ptr = base + off; off += (bytes + 255) & ~(size_t)255; return ptr; };
+    double *V = reinterpret_cast<double *>(take((size_t)n * BW * 8));
+    double *T = reinterpret_cast<double *>(take((size_t)BW * BW * 8));
+    double *R = reinterpret_cast<double *>(take((size_t)BW * BW * 8));
+    double *P = reinterpret_cast<double *>(take(2 * (size_t)rows * BW * 8));
+    double *W1 = reinterpret_cast<double *>(take((size_t)BW * kp * 8));
+    double *W2 = reinterpret_cast<double *>(take((size_t)BW * kp * 8));
+    double *gbuf = reinterpret_cast<double *>(take(3 * BW * 8));
+    double *rowk = reinterpret_cast<double *>(take(3 * BW * 8));
+    unsigned int *counter = reinterpret_cast<unsigned int *>(take(256));
+    PanelScratch ps{gbuf, rowk, counter, false, sm_count()};
+    int rc;
+    if ((rc = panel_qr_setup(ps)) != GNNGP_OK) return rc;
+    for (int64_t q = 0; q * BW < kp; ++q) {
+        const int64_t r0 = q * BW, s = n - r0;              // the panel: rows r0.., columns r0 .. r0 + BW
+        if (s <= 0) break;
+        if ((rc = panel_qr(z + r0 * ldz + r0, ldz, s, V, R, T, ps, st)) != GNNGP_OK) return rc;
+        const int64_t nc = kp - (r0 + BW);                  // columns of Z still to be factorised
+        if (nc > 0) {
+            double *A2 = z + r0 * ldz + (r0 + BW);
+            // W1 = V^T A2   (BW x nc, contraction over the s rows)
+            const int sp = splits_for(BW, nc, s);
+            if (sp > 1) GNNGP_CUDA(cudaMemsetAsync(W1, 0, (size_t)BW * nc * 8, st));
+            if ((rc = dgemm(BW, nc, s, View{V, 1, BW}, View{A2, ldz, 1}, 0, kNoView, kNoView, 1.0, 0.0, W1, nc, sp, st)) != GNNGP_OK) return rc;
+            // W2 = T^T W1 ;  A2 -= V W2                    (Q_p^T applied from the left)
+            if ((rc = dgemm(BW, nc, BW, View{T, 1, BW}, View{W1, nc, 1}, 0, kNoView, kNoView, 1.0, 0.0, W2, nc, 1, st)) != GNNGP_OK) return rc;
+            if ((rc = dgemm(s, nc, BW, View{V, BW, 1}, View{W2, nc, 1}, 0, kNoView, kNoView, -1.0, 1.0, A2, ldz, 1, st)) != GNNGP_OK) return rc;
+        }
+        // X[:, r0:] <- X[:, r0:] (I - V T V^T)
+        if ((rc = apply_reflector(x, ldx, rows, r0, s, V, T, false, P, st)) != GNNGP_OK) return rc;
+    }
     return GNNGP_OK;
 }

@@ -8,18 +8,26 @@ the clamp ``f`` is LINEAR, ``f(lam) = lam / tau^2``, hence
 
     f(M) = M / tau^2 + V_t diag(1/lam - lam/tau^2) V_tᵀ            (V_t, lam: the eigenpairs ABOVE tau only)
 
-and with the Cholesky factor ``M = L Lᵀ`` the matrix
+and with the Cholesky factor ``M = L Lᵀ``, ``Z = Lᵀ V_t diag(lam)^-1/2`` (orthonormal columns) and ANY orthogonal
+``Q_H = [Z | Z_perp]`` (here: the Householder QR of ``Z``) the matrices
 
-    S = L / tau + V_t diag(1/lam - 1/tau) V_tᵀ L                    satisfies  S Sᵀ = f(M)  and  M S = ... = L-consistent:
+    B = L Q_H          (B Bᵀ = M;  columns j < k are ± V_t sqrt(lam_j))
+    S = B diag(s),     s_j = 1/lam_j (j < k),  1/tau (j >= k)        satisfy  S Sᵀ = f(M):
 
-``Q[mask] = L`` and ``Q[~mask] = K[~mask] S`` is the reference's factor times one orthogonal matrix (``R = S_ref⁻¹ S``).
+``Q[mask] = B`` and ``Q[~mask] = K[~mask] S`` is the reference's factor times one orthogonal matrix (``R = S_ref⁻¹ S``).
+The leading k columns are EXACTLY the reference's columns for the eigenvalues above the clamp (graded like ``sqrt(D)`` /
+``1/sqrt(D)``), the other n-k columns an orthogonal mix of the directions below it (whose scales differ by < 4x).  The
+grading matters downstream: the fit's Gram matrix ``Q_bᵀQ_b`` is formed in fp32-equivalent arithmetic, whose elementwise
+relative error preserves the small eigenvalues only when the columns carry their own scales — an ungraded ``S`` (e.g.
+``S = L/tau + V_t diag(1/lam - 1/tau) V_tᵀ L``, tried first) made ``Q_bᵀQ_b + eps d I`` numerically indefinite at the
+small nuggets.
 On the benchmark graph 647 of 15 404 eigenvalues lie above the clamp: instead of a 15 404² eigendecomposition
 (cuSOLVER fp64: 2.28 s on B200, bound by the one-stage tridiagonalisation) the route needs
 
   * one dense fp64 Cholesky factorisation (n³/3 flops, blocked, own DMMA GEMM),
   * the eigenpairs above ``tau`` from a block Lanczos process with full re-orthogonalisation (block 128, Krylov
     dimension ~0.11 n; every product ``M V_j`` is one fp64 GEMM) and a Rayleigh–Ritz step on the small projected matrix,
-  * three skinny GEMMs that assemble ``Sᵀ``.
+  * one skinny GEMM for ``Z``, a Householder QR of the n x k block ``Z`` and its block reflectors applied to ``L``.
 
 Everything is fp64: ``S`` cancels ``L / tau`` against the top of the spectrum (1/tau against 1/lam_max = 1e-4 / tau), which
 needs the top Ritz vectors to ~1e-10; a Ritz pair (theta, y) is accepted when ``|M y - theta y| <= tol * tau * theta_max /
@@ -40,6 +48,7 @@ from typing import Optional, Tuple
 
 import torch
 
+PANEL = 128                      # panel width of the Householder QR kernels (csrc/bandfit.cu)
 DEFAULT_BLOCK = 128              # Lanczos block = the Cholesky panel width of csrc/dense64.cu
 CLAMP = 1e-4                     # src/compute.py:13
 RESIDUAL_TOL = 1e-7              # see the module docstring
@@ -209,15 +218,20 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases):
     phases.mark("ritz_vectors")
     if not worst <= 1.0:
         return None
-    # ---- S^T = L^T / tau + (L^T V_t) diag(1/theta - 1/tau) V_t^T          (V_t: the k Ritz vectors above the clamp)
-    vt = ritz[:, k_check - k:]
-    weights = (1.0 / sel[k_check - k:] - 1.0 / tau).to(dev)
-    st = ops.transpose_scale_f64(chol, 1.0 / tau)
+    # ---- rotate the Cholesky factor into the graded basis: B = L Q_H with Q_H = [Z | Z_perp], Z = L^T V_t Theta^-1/2
+    vt = ritz[:, k_check - k:]                                       # the k Ritz vectors above the clamp
+    theta_t = sel[k_check - k:]
+    k_pad = -(-max(k, 1) // PANEL) * PANEL
+    if k_pad > n:
+        return None
+    z = torch.zeros((n, k_pad), dtype=f64, device=dev)
     if k > 0:
-        p = resid[:, :k]                                             # [n x k] scratch (the residuals are spent)
-        ops.dgemm(chol.T, vt, out=p)
-        vw = ops.scale_cols_f64(vt, weights)
-        ops.dgemm(p, vw.T, out=st, beta=1.0)
+        vs = ops.scale_cols_f64(vt, torch.rsqrt(theta_t).to(dev))
+        ops.dgemm(chol.T, vs, out=z[:, :k])
+    ops.qr_rotate(chol, z)                                           # chol <- L Q_H: columns j < k are +-V_t sqrt(theta_j)
+    scale = torch.full((n,), 1.0 / tau, dtype=f64)
+    scale[:k] = 1.0 / theta_t
+    st = ops.transpose_scale_f64(ops.scale_cols_f64(chol, scale.to(dev)), 1.0)
     out = ops.to_f32(st), ops.to_f32(chol)
     phases.mark("assemble")
     return out

@@ -572,6 +572,21 @@ class CudaOps(object):
                       self._stream())
         return linv
 
+    def qr_rotate(self, X: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+        """``X <- X Q_H`` in place, ``Q_H`` the orthogonal factor of the Householder QR of ``Z`` [n x kp] (kp a multiple of
+        128; ``Z`` is overwritten)."""
+        self._f64_view(X, "X"), self._f64_view(Z, "Z")
+        rows, n = X.shape
+        n2, kp = Z.shape
+        if n2 != n or X.stride(1) != 1 or Z.stride(1) != 1:
+            raise RuntimeError("qr_rotate: X [rows x n] and Z [n x kp] row-major expected")
+        need = self.lib.query("gnngp_qr_rotate_workspace_bytes", rows, n, kp)
+        ws = self.workspace(need + 256, X.device, "qr_rotate")
+        wptr = (ws.data_ptr() + 255) // 256 * 256
+        self.lib.call("gnngp_qr_rotate_f64", X.data_ptr(), X.stride(0), rows, Z.data_ptr(), Z.stride(0), n, kp, wptr, need,
+                      self._stream())
+        return X
+
     def eigh_small_f64(self, H: torch.Tensor):
         """Rayleigh-Ritz step of the Krylov root: eigendecomposition of the SMALL projected matrix (dimension ~0.11 n;
         cuSOLVER through torch, 1/200 of the flops of the eigendecomposition it replaces)."""

@@ -105,7 +105,7 @@ class Pipeline(object):
         if krylov_root.wanted(kmm.shape[0], ops):
             stats = {}
             got = krylov_root.root_factors(ops, kmm, stats)
-            self.last_root_stats = stats
+            self.last_root_stats = ops.last_root_stats = stats
             if got is not None:
                 self.last_root_solver = ops.last_root_solver = "krylov"
                 return got

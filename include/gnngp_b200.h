@@ -234,7 +234,13 @@ int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, const float *r
  *   potrf_inv_block_f64  one block of nb <= 128 rows: L in place and, when linv != NULL, L^-1 (full nb x nb, zeros above)
  *   residual_sumsq_f64   out[j] = sum_i (r[i][j] - theta[j] v[i][j])^2  (Ritz residuals |M y - theta y|^2)
  *   transpose_scale_f64  out[j][i] = alpha a[i][j];  scale_cols_f64  out[i][j] = v[i][j] d[j];  f64_to_f32  dst = (float)src
+ *   qr_rotate_f64        x[rows x n] <- x Q_H with Q_H the orthogonal factor of the Householder QR of z [n x kp] (kp a
+ *                        multiple of 128, z overwritten): the leading columns of x Q_H are +-(x z_j) for orthonormal z_j,
+ *                        the others x times an orthonormal basis of the complement (csrc/bandfit.cu panel kernels)
  * No host synchronisation in any of them. */
+size_t gnngp_qr_rotate_workspace_bytes(int64_t rows, int64_t n, int64_t kp);
+int gnngp_qr_rotate_f64(double *x, int64_t ldx, int64_t rows, double *z, int64_t ldz, int64_t n, int64_t kp,
+                        void *workspace, size_t workspace_bytes, gnngp_stream_t stream);
 int gnngp_sym_f64_from_f32(const float *g, int64_t ldg, int64_t n, double *a, int64_t lda, gnngp_stream_t stream);
 int gnngp_dgemm_f64(int64_t m, int64_t n, int64_t k, const double *a, int64_t a_rs, int64_t a_cs, const double *b,
                     int64_t b_rs, int64_t b_cs, double alpha, double beta, double *c, int64_t ldc, int lower,

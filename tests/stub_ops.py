@@ -159,6 +159,11 @@ class StubOps(object):
             return torch.eye(G.shape[0], dtype=G.dtype)
         return torch.linalg.solve_triangular(G, torch.eye(G.shape[0], dtype=G.dtype), upper=False)
 
+    def qr_rotate(self, X, Z):
+        q, _ = torch.linalg.qr(Z, mode="complete")
+        X.copy_(X @ q)
+        return X
+
     def eigh_small_f64(self, H):
         return torch.linalg.eigh(H)
 

@@ -102,6 +102,25 @@ def test_small_helpers(ops):
     assert rel(got, ((a - v * d) ** 2).sum(0)) < 1e-13
 
 
+@pytest.mark.parametrize("rows,n,k", [(300, 1000, 128), (2500, 2500, 300), (700, 4000, 647)])
+def test_qr_rotate(ops, rows, n, k):
+    """X Q_H: an orthogonal transformation whose leading columns are +-(X z_j) for orthonormal z_j."""
+    gen = torch.Generator(device=DEV).manual_seed(rows + n + k)
+    zq, _ = torch.linalg.qr(torch.randn(n, k, device=DEV, dtype=torch.float64, generator=gen))
+    kp = -(-k // 128) * 128
+    z = torch.zeros(n, kp, device=DEV, dtype=torch.float64)
+    z[:, :k] = zq
+    x0 = torch.randn(rows, n, device=DEV, dtype=torch.float64, generator=gen)
+    x = x0.clone()
+    ops.qr_rotate(x, z)
+    assert rel(x @ x.T, x0 @ x0.T) < 1e-12                                     # orthogonal
+    lead = x0 @ zq
+    assert rel(x[:, :k].abs(), lead.abs()) < 1e-11
+    assert rel(x[:, :k] * torch.sign((x[:, :k] * lead).sum(0)), lead) < 1e-11
+    rest = x[:, k:]                                                            # = X Z_perp: orthogonal to the lead block's range
+    assert rel(rest @ rest.T + lead @ lead.T, x0 @ x0.T) < 1e-11
+
+
 def _block(n, above, seed=0, gap=0.5):
     gen = torch.Generator(device=DEV).manual_seed(seed)
     q, _ = torch.linalg.qr(torch.randn(n, n, device=DEV, dtype=torch.float64, generator=gen))
