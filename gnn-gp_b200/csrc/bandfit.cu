@@ -732,11 +732,15 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
         band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
         GNNGP_LAUNCHED();
         double *A22 = A + r0 * lda + r0;
-        // Y = A22 V   (a skinny output: K is split so that the grid covers the chip)
+        // Y = A22 V with A22 symmetric and valid only in the tiles that touch its lower triangle (the update below skips
+        // the others): row block m0 takes k < m0 + 128 from the matrix and k >= m0 + 128 from the transposed view.
+        // A skinny output: K is split so that the grid covers the chip, both passes accumulate into the zeroed Y.
         {
-            const int sp = splits_for(s, BW, s);
-            if (sp > 1) GNNGP_CUDA(cudaMemsetAsync(Y, 0, (size_t)s * BW * 8, st));
-            if ((rc = dgemm(s, BW, s, View{A22, lda, 1}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 0.0, Y, BW, sp, st)) != GNNGP_OK) return rc;
+            const int sp = std::max(1, splits_for(s, BW, s / 2));
+            GNNGP_CUDA(cudaMemsetAsync(Y, 0, (size_t)s * BW * 8, st));
+            if ((rc = dgemm(s, BW, s, View{A22, lda, 1}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 1.0, Y, BW, sp, st, 0, 1)) != GNNGP_OK) return rc;
+            if (s > BW &&
+                (rc = dgemm(s, BW, s, View{A22, 1, lda}, View{Vp, BW, 1}, 0, kNoView, kNoView, 1.0, 1.0, Y, BW, sp, st, 0, 2)) != GNNGP_OK) return rc;
         }
         // M1 = V^T Y
         {
@@ -749,8 +753,8 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
         if ((rc = dgemm(BW, BW, BW, View{Tq, 1, BW}, View{tmp, BW, 1}, 0, kNoView, kNoView, -0.5, 0.0, M2, BW, 1, st)) != GNNGP_OK) return rc;
         // W = Y T + V M2
         if ((rc = dgemm(s, BW, BW, View{Y, BW, 1}, View{Tq, BW, 1}, BW, View{Vp, BW, 1}, View{M2, BW, 1}, 1.0, 0.0, W, BW, 1, st)) != GNNGP_OK) return rc;
-        // A22 -= V W^T + W V^T        B(k, j) = W[j][k] / V[j][k]
-        if ((rc = dgemm(s, s, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st)) != GNNGP_OK) return rc;
+        // A22 -= V W^T + W V^T        B(k, j) = W[j][k] / V[j][k]; only the tiles that touch the lower triangle
+        if ((rc = dgemm(s, s, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st, 1)) != GNNGP_OK) return rc;
         // right-hand sides: rhs[:, r0:] <- rhs[:, r0:] (I - V T V^T)   (= (Q_p^T c)^T)
         if ((rc = apply_reflector(rhs, m, C, r0, s, Vp, Tq, false, P, st)) != GNNGP_OK) return rc;
         Vp += s * BW;

@@ -36,6 +36,26 @@ def test_dgemm_views_against_torch(ops, m, n, k):
                 assert torch.equal(out[:, n:], c0[:, n:])                  # columns outside the view untouched
 
 
+@pytest.mark.parametrize("m,n,k", [(257, 130, 1000), (129, 66, 77), (1000, 64, 3), (127, 63, 17), (1, 1, 1), (2, 3, 16), (300, 129, 32),
+                                   (4000, 128, 4001), (128, 128, 40001)])
+def test_dgemm_aligned_views_take_the_fast_path(ops, m, n, k):
+    """16-byte aligned operands with even strides (the layouts the band reduction and the Krylov root use): all four
+    layout combinations, ragged M / N / K edges, split-K and read-modify-write epilogues."""
+    gen = torch.Generator(device=DEV).manual_seed(m * 5 + n * 11 + k)
+    e = lambda x: x + (x & 1)                                                  # even
+    big_a = torch.randn(e(max(m, k)) + 6, e(max(m, k)) + 8, device=DEV, dtype=torch.float64, generator=gen)
+    big_b = torch.randn(e(max(n, k)) + 4, e(max(n, k)) + 10, device=DEV, dtype=torch.float64, generator=gen)
+    c0 = torch.randn(m, e(n) + 4, device=DEV, dtype=torch.float64, generator=gen)
+    for a in (big_a[2:2 + m, 4:4 + k], big_a[2:2 + k, 4:4 + m].T):
+        for b in (big_b[4:4 + k, 2:2 + n], big_b[2:2 + n, 6:6 + k].T):
+            for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)):
+                out = c0.clone()
+                ops.dgemm(a, b, out=out[:, :n], alpha=alpha, beta=beta)
+                want = alpha * (a @ b) + beta * c0[:, :n]
+                assert rel(out[:, :n], want) < 1e-13, (m, n, k, alpha, beta, a.stride(), b.stride())
+                assert torch.equal(out[:, n:], c0[:, n:])
+
+
 def test_dgemm_lower_updates_the_lower_triangle(ops):
     gen = torch.Generator(device=DEV).manual_seed(11)
     n, k = 777, 128
