@@ -583,10 +583,10 @@ static Plan make_plan(int64_t m, int64_t C, int64_t G)
     p.off_rowk = take((size_t)3 * BW * 8);
     p.off_counter = take(256);
     p.off_Bd = take((size_t)m * (BW + 1) * 8);
-    p.off_rhs = take((size_t)C * m * 8);
+    p.off_rhs = take((size_t)C * p.lda * 8);               // vectors as rows, even pitch (the fp64 GEMM's aligned fast path)
     p.off_P = take((size_t)G * C * BW * 8);
     p.off_L = take((size_t)G * m * (BW + 1) * 8);
-    p.off_sol = take((size_t)G * C * m * 8);
+    p.off_sol = take((size_t)G * C * p.lda * 8);
     p.total = off + 256;
     return p;
 }
@@ -717,7 +717,7 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     GNNGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     symmetrize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(m * m, 256), (int64_t)sms * 16), 256, 0, st>>>(gram, ldg, m, A, lda);
     GNNGP_LAUNCHED();
-    to_f64_kernel<<<(unsigned)std::min<int64_t>(ceil_div(C * m, 256), (int64_t)sms * 8), 256, 0, st>>>(rhs_t, ldr, C, m, rhs, m);
+    to_f64_kernel<<<(unsigned)std::min<int64_t>(ceil_div(C * m, 256), (int64_t)sms * 8), 256, 0, st>>>(rhs_t, ldr, C, m, rhs, lda);
     GNNGP_LAUNCHED();
 
     // ---- band reduction, one panel at a time; the right-hand sides are transformed along the way (Q_p^T)
@@ -756,7 +756,7 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
         // A22 -= V W^T + W V^T        B(k, j) = W[j][k] / V[j][k]; only the tiles that touch the lower triangle
         if ((rc = dgemm(s, s, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st, 1)) != GNNGP_OK) return rc;
         // right-hand sides: rhs[:, r0:] <- rhs[:, r0:] (I - V T V^T)   (= (Q_p^T c)^T)
-        if ((rc = apply_reflector(rhs, m, C, r0, s, Vp, Tq, false, P, st)) != GNNGP_OK) return rc;
+        if ((rc = apply_reflector(rhs, lda, C, r0, s, Vp, Tq, false, P, st)) != GNNGP_OK) return rc;
         Vp += s * BW;
     }
     // last block: already inside the band
@@ -769,7 +769,7 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     {
         const size_t smem = (size_t)(SLOTS * RHS_LD + 2 * CH * (WIN + RHS_MAX) + WIN + RHS_MAX + WIN) * sizeof(double);
         GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(band_cholesky_solve_kernel), (int)smem));
-        band_cholesky_solve_kernel<<<(unsigned)G, SOLVE_THREADS, smem, st>>>(Bd, m, shifts, rhs, m, (int)C, Lg, sol, m, info);
+        band_cholesky_solve_kernel<<<(unsigned)G, SOLVE_THREADS, smem, st>>>(Bd, m, shifts, rhs, lda, (int)C, Lg, sol, lda, info);
         GNNGP_LAUNCHED();
     }
     // ---- solutions back to the original basis: sol <- sol Q_p^T for p = last .. 0   (x = Q_0 Q_1 ... z)
@@ -778,9 +778,9 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     for (int64_t q = 0; q < p.panels; ++q) { vptr[q] = Vp; Vp += (m - (q + 1) * BW) * BW; }
     for (int64_t q = p.panels - 1; q >= 0; --q) {
         const int64_t r0 = (q + 1) * BW, s = m - r0;
-        if ((rc = apply_reflector(sol, m, G * C, r0, s, vptr[q], Tall + q * BW * BW, true, P, st)) != GNNGP_OK) return rc;
+        if ((rc = apply_reflector(sol, lda, G * C, r0, s, vptr[q], Tall + q * BW * BW, true, P, st)) != GNNGP_OK) return rc;
     }
-    to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(G * C * m, 256), (int64_t)sms * 16), 256, 0, st>>>(sol, m, G * C, m, coeff_t, ldo);
+    to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(G * C * m, 256), (int64_t)sms * 16), 256, 0, st>>>(sol, lda, G * C, m, coeff_t, ldo);
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }

@@ -24,11 +24,13 @@ using f64::splits_for;
 constexpr int NB = 128;                 // Cholesky panel = largest block of potrf_inv_block
 constexpr int LDB = NB + 1;             // odd pitch: column walks hit distinct banks
 constexpr int PT = 1024;                // threads of the block kernel
+constexpr int JB = 16;                  // inner block of the one-CTA factorisation
 
 // ---------------------------------------------------------------------------------------------
 // One CTA: Cholesky factor of an nb x nb block (lower triangle of A, in place) and its inverse.
-// Factorisation: right-looking, the block in shared memory; per column one broadcast read of the pivot, a scaled
-// column and a rank-1 update of the trailing lower triangle spread over 32 x 32 threads.  A non-positive pivot is
+// Factorisation: blocked right-looking in shared memory, 16 columns per step (the first version did one column per step:
+// three block barriers, a redundant sqrt / division in every warp and a rank-1 update per column — 206 us per block,
+// 31 ms of the 210 ms Krylov root, profiles/r2/call18_launches_root_summary.txt).  A non-positive pivot is
 // counted in `info` and replaced by 1 so that the kernel finishes with finite numbers (the caller discards them).
 // Inverse: column c of X = L^-1 by forward substitution, 8 lanes per column sharing each dot product; X^T lives in the
 // strict upper triangle of the same shared-memory block (free after the factorisation), its diagonal in `dinv`.
@@ -45,22 +47,82 @@ potrf_inv_block_kernel(double *__restrict__ A, int64_t lda, int nb, double *__re
     for (int i = ty; i < nb; i += 32)
         for (int j = tx; j < nb; j += 32) sm[i * LDB + j] = (j <= i) ? A[i * lda + j] : 0.0;
     __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        const double d = sm[j * LDB + j];
-        const bool ok = d > 0.0;
-        const double r = ok ? sqrt(d) : 1.0;
-        const double inv = 1.0 / r;
-        __syncthreads();                                     // every thread holds the pivot before it is overwritten
-        if (t == 0) {
-            sm[j * LDB + j] = r;
-            dinv[j] = inv;
-            if (!ok) bad_s = 1;
+    // blocked right-looking factorisation, JB columns at a time: (1) warp 0 factorises the JB x JB diagonal block,
+    // (2) one thread per row below it solves its JB entries by forward substitution, (3) all threads apply the rank-JB
+    // update to the trailing lower triangle from register tiles (rows ty + 32 a, columns tx + 32 b: consecutive lanes
+    // read consecutive rows of the odd-pitch block — conflict-free — and a warp's row operand is a broadcast).
+    for (int jb = 0; jb < nb; jb += JB) {
+        const int w = min(JB, nb - jb);
+        if (ty == 0) {
+            for (int c = 0; c < w; ++c) {
+                const double d = sm[(jb + c) * LDB + jb + c];
+                const bool ok = d > 0.0;
+                const double r = ok ? sqrt(d) : 1.0;
+                const double inv = 1.0 / r;
+                __syncwarp();                                // every lane holds the pivot before it is overwritten
+                if (tx == 0) {
+                    sm[(jb + c) * LDB + jb + c] = r;
+                    dinv[jb + c] = inv;
+                    if (!ok) bad_s = 1;
+                }
+                if (tx > c && tx < w) sm[(jb + tx) * LDB + jb + c] *= inv;
+                __syncwarp();
+                for (int e = tx; e < w * w; e += 32) {
+                    const int r2 = e / w, c2 = e - r2 * w;
+                    if (c2 > c && c2 <= r2)
+                        sm[(jb + r2) * LDB + jb + c2] = fma(-sm[(jb + r2) * LDB + jb + c], sm[(jb + c2) * LDB + jb + c], sm[(jb + r2) * LDB + jb + c2]);
+                }
+                __syncwarp();
+            }
         }
-        for (int i = j + 1 + t; i < nb; i += PT) sm[i * LDB + j] *= inv;
         __syncthreads();
-        for (int i = j + 1 + ty; i < nb; i += 32) {
-            const double lij = sm[i * LDB + j];
-            for (int l = j + 1 + tx; l <= i; l += 32) sm[i * LDB + l] = fma(-lij, sm[l * LDB + j], sm[i * LDB + l]);
+        const int r0 = jb + w, rem = nb - r0;                // first trailing row, trailing rows
+        if (t < rem) {
+            double x[JB];
+            double *row = sm + (r0 + t) * LDB + jb;
+#pragma unroll
+            for (int c = 0; c < JB; ++c) {
+                if (c < w) {
+                    double v = row[c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) v = fma(-x[m], sm[(jb + c) * LDB + jb + m], v);
+                    x[c] = v * dinv[jb + c];
+                } else {
+                    x[c] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < JB; ++c)
+                if (c < w) row[c] = x[c];
+        }
+        __syncthreads();
+        if (rem > 0) {
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+            for (int c = 0; c < w; ++c) {
+                double pi[4], pl[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int i = ty + 32 * a, l = tx + 32 * a;
+                    pi[a] = (i < rem) ? sm[(r0 + i) * LDB + jb + c] : 0.0;
+                    pl[a] = (l < rem) ? sm[(r0 + l) * LDB + jb + c] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b <= a; ++b)
+                        if (32 * a < rem) acc[a][b] = fma(pi[a], pl[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    const int i = ty + 32 * a, l = tx + 32 * b;
+                    if (i < rem && l <= i) sm[(r0 + i) * LDB + r0 + l] -= acc[a][b];
+                }
         }
         __syncthreads();
     }

@@ -64,7 +64,7 @@ def wanted(n: int, ops) -> bool:
     if mode == "eigh" or not hasattr(ops, "dgemm"):
         return False
     if mode == "krylov":
-        return n >= 2 * DEFAULT_BLOCK
+        return n >= 2 * int(os.environ.get("GNNGP_ROOT_BLOCK", DEFAULT_BLOCK))
     return n >= 4096
 
 
@@ -204,8 +204,9 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases):
         return None
     sel = theta_host[dim - k_check:]
     y_sel = y[:, dim - k_check:]
-    ritz = torch.empty((n, k_check), dtype=f64, device=dev)
-    resid = torch.empty((n, k_check), dtype=f64, device=dev)
+    pitch = k_check + (k_check & 1)                                  # even row pitch: the fp64 GEMM's aligned fast path
+    ritz = torch.empty((n, pitch), dtype=f64, device=dev)[:, :k_check]
+    resid = torch.empty((n, pitch), dtype=f64, device=dev)[:, :k_check]
     ops.dgemm(basis, y_sel, out=ritz)
     ops.dgemm(mbasis, y_sel, out=resid)
     theta_dev = sel.to(dev)
@@ -226,7 +227,8 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases):
         return None
     z = torch.zeros((n, k_pad), dtype=f64, device=dev)
     if k > 0:
-        vs = ops.scale_cols_f64(vt, torch.rsqrt(theta_t).to(dev))
+        vs = torch.empty((n, k + (k & 1)), dtype=f64, device=dev)[:, :k]
+        ops.scale_cols_f64(vt, torch.rsqrt(theta_t).to(dev), out=vs)
         ops.dgemm(chol.T, vs, out=z[:, :k])
     ops.qr_rotate(chol, z)                                           # chol <- L Q_H: columns j < k are +-V_t sqrt(theta_j)
     scale = torch.full((n,), 1.0 / tau, dtype=f64)

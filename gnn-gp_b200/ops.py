@@ -609,12 +609,13 @@ class CudaOps(object):
                       self._stream())
         return out
 
-    def scale_cols_f64(self, V: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    def scale_cols_f64(self, V: torch.Tensor, d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._f64_view(V, "V")
         rows, cols = V.shape
         d = d.contiguous()
-        out = torch.empty((rows, cols), dtype=torch.float64, device=V.device)
-        self.lib.call("gnngp_scale_cols_f64", V.data_ptr(), V.stride(0), rows, cols, d.data_ptr(), out.data_ptr(), cols,
+        if out is None:
+            out = torch.empty((rows, cols), dtype=torch.float64, device=V.device)
+        self.lib.call("gnngp_scale_cols_f64", V.data_ptr(), V.stride(0), rows, cols, d.data_ptr(), out.data_ptr(), out.stride(0),
                       self._stream())
         return out
 

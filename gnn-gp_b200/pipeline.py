@@ -569,10 +569,10 @@ class Pipeline(object):
             return "eigh"
         per_rank = (n_nuggets + world - 1) // world
         if band_ok:
-            # replicated band reduction (every rank solves all nuggets; measured 43 ms at m = 3 053, 111 ms at 6 138,
-            # 0.71 s at 15 405, profiles/r2) against this rank's share of dense factorisations (potrf + substitution:
-            # 1.7 ms at 3 025, 5.2 ms at 6 138, 47 ms at 15 356 per nugget)
-            band_ms = 43.0 * (m / 3053.0) ** 1.75
+            # replicated band reduction (every rank solves all nuggets; measured 41 ms at m = 3 053, 99 ms at 6 138,
+            # 486 ms at 15 405, profiles/r2/call17_bandfit_probe.json) against this rank's share of dense factorisations
+            # (potrf + substitution: 1.7 ms at 3 025, 5.2 ms at 6 138, 47 ms at 15 356 per nugget)
+            band_ms = 41.0 * (m / 3053.0) ** 1.53
             chol_ms = per_rank * 1.7 * (m / 3025.0) ** 2.05
             return "band" if band_ms <= chol_ms else "cholesky"
         return "cholesky" if per_rank < 30.0 * (m / 3025.0) ** 0.3 else "eigh"

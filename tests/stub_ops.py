@@ -173,8 +173,12 @@ class StubOps(object):
     def transpose_scale_f64(self, A, alpha):
         return (alpha * A.T).contiguous()
 
-    def scale_cols_f64(self, V, d):
-        return V * d.view(1, -1)
+    def scale_cols_f64(self, V, d, out=None):
+        res = V * d.view(1, -1)
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
 
     def to_f32(self, A):
         out = self.empty(A.shape[0], A.shape[1])

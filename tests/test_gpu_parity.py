@@ -66,6 +66,24 @@ def test_public_api_matches_live_oracle(name):
     assert abs(float(out["summary"]["val"]) - ref["summary"]["val"]) <= 2.5 / max(int(masks["val"].sum()), 1) + 2e-3
 
 
+@pytest.mark.parametrize("name", ["pubmed-GCN-nys4-L2", "small-GCN-nys4-L2", "small-SAGE-nys4-L4", "chameleon-GCN2-nys1-L2"])
+def test_krylov_root_route_matches_reference_golden(name, monkeypatch):
+    """The Nystrom root without a full eigendecomposition (krylov_root.py: Cholesky factor + block Lanczos for the
+    eigenpairs above the clamp, csrc/dense64.cu) forced on mid-size landmark blocks with a small Lanczos block: same
+    golden check as the eigen route.  Blocks whose spectrum lies mostly above the clamp are handed back to ``eigh`` by
+    the route itself — at least the PubMed-shape block (1 479 landmarks) must be solved by it."""
+    from gnngp_b200.ops import default_ops
+    monkeypatch.setenv("GNNGP_ROOT_SOLVER", "krylov")
+    monkeypatch.setenv("GNNGP_ROOT_BLOCK", "32")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    default_ops().last_root_solver = None
+    out, _ = run_public_api(case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+    if name.startswith("pubmed"):
+        assert default_ops().last_root_solver == "krylov", getattr(default_ops(), "last_root_stats", None)
+
+
 @pytest.mark.parametrize("name", ["small-GCN-nys4-L2", "tinyreg-GIN-nys1-L3", "pubmed-GCN-nys4-L2", "chameleon-SAGE-nys1-L2"])
 def test_nugget_parallel_fit_matches_reference_golden(name, monkeypatch):
     """The sharded mode's fit route (fp64 potrf per nugget + the batched substitution kernel) forced on one

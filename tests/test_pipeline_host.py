@@ -79,9 +79,9 @@ def test_fit_solver_policy(monkeypatch):
     assert Pipeline(StubOps(), Comm(1))._fit_solver(31000, 101, 41) == "eigh"    # beyond the shared-memory panel
     assert Pipeline(StubOps(), Comm(2))._fit_solver(3025, 101, 41) == "band"     # 51 dense solves per rank cost more
     assert Pipeline(StubOps(), Comm(2))._fit_solver(15356, 101, 41) == "band"
-    assert Pipeline(StubOps(), Comm(4))._fit_solver(15356, 101, 41) == "band"    # 26 x 47 ms > 0.71 s
-    assert Pipeline(StubOps(), Comm(8))._fit_solver(3025, 101, 41) == "cholesky" # 13 x 1.7 ms < 43 ms
-    assert Pipeline(StubOps(), Comm(8))._fit_solver(15356, 101, 41) == "cholesky"
+    assert Pipeline(StubOps(), Comm(4))._fit_solver(15356, 101, 41) == "band"    # 26 x 47 ms > 0.49 s
+    assert Pipeline(StubOps(), Comm(8))._fit_solver(3025, 101, 41) == "cholesky" # 13 x 1.7 ms < 41 ms
+    assert Pipeline(StubOps(), Comm(8))._fit_solver(15356, 101, 41) == "band"    # 13 x 47 ms > 0.49 s
     assert Pipeline(StubOps(), Comm(4))._fit_solver(3025, 101, 100) == "cholesky"  # too many targets for the band kernel
     assert Pipeline(StubOps(), Comm(8))._fit_solver(604, 101) == "eigh"          # small block: eigh is cheap
     monkeypatch.setenv("GNNGP_FIT_SOLVER", "cholesky")
