@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -667,6 +668,34 @@ static int panel_qr(const double *Ap, int64_t lda, int64_t s, double *Vp, double
     return GNNGP_OK;
 }
 
+// side stream + events of the band reduction's look-ahead, one set per device (created on first use, never destroyed)
+struct LookAhead { cudaStream_t side; cudaEvent_t cols_done, panel_done; bool on; };
+
+static int lookahead_setup(LookAhead &la)
+{
+    static LookAhead per_device[64] = {};
+    static bool made[64] = {};
+    int dev = 0;
+    GNNGP_CUDA(cudaGetDevice(&dev));
+    const char *env = getenv("GNNGP_BAND_LOOKAHEAD");
+    const bool want = !(env && env[0] == '0');
+    if (dev < 0 || dev >= 64 || !want) {
+        la = LookAhead{nullptr, nullptr, nullptr, false};
+        return GNNGP_OK;
+    }
+    if (!made[dev]) {
+        int lo = 0, hi = 0;
+        GNNGP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        GNNGP_CUDA(cudaStreamCreateWithPriority(&per_device[dev].side, cudaStreamNonBlocking, hi));
+        GNNGP_CUDA(cudaEventCreateWithFlags(&per_device[dev].cols_done, cudaEventDisableTiming));
+        GNNGP_CUDA(cudaEventCreateWithFlags(&per_device[dev].panel_done, cudaEventDisableTiming));
+        per_device[dev].on = true;
+        made[dev] = true;
+    }
+    la = per_device[dev];
+    return GNNGP_OK;
+}
+
 }  // namespace bandfit
 }  // namespace gnngp
 
@@ -723,14 +752,26 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
     // ---- band reduction, one panel at a time; the right-hand sides are transformed along the way (Q_p^T)
     PanelScratch ps{gbuf, rowk, counter, false, sms};
     if ((rc = panel_qr_setup(ps)) != GNNGP_OK) return rc;
+    // Look-ahead: the QR of panel q+1 only needs the first BW columns of the updated trailing matrix, so the update is
+    // split — those columns first, then the rest — and the next panel (a latency-bound kernel: one grid barrier per
+    // column, ~1 ms per panel) is factorised on a high-priority side stream while the rest of the update runs.
+    // GNNGP_BAND_LOOKAHEAD=0 restores the serial order.
+    LookAhead la;
+    if ((rc = lookahead_setup(la)) != GNNGP_OK) return rc;
     double *Vp = Vall;
+    bool have_panel = false;                                // V, T of panel q already computed by the look-ahead
     for (int64_t q = 0; q < p.panels; ++q) {
         const int64_t j0 = q * BW, r0 = j0 + BW, s = m - r0;
         const double *Ap = A + r0 * lda + j0;
         double *Tq = Tall + q * BW * BW;
-        if ((rc = panel_qr(Ap, lda, s, Vp, R, Tq, ps, st)) != GNNGP_OK) return rc;
-        band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
-        GNNGP_LAUNCHED();
+        if (have_panel) {
+            GNNGP_CUDA(cudaStreamWaitEvent(st, la.panel_done, 0));
+        } else {
+            if ((rc = panel_qr(Ap, lda, s, Vp, R, Tq, ps, st)) != GNNGP_OK) return rc;
+            band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 1, Bd);
+            GNNGP_LAUNCHED();
+        }
+        have_panel = false;
         double *A22 = A + r0 * lda + r0;
         // Y = A22 V with A22 symmetric and valid only in the tiles that touch its lower triangle (the update below skips
         // the others): row block m0 takes k < m0 + 128 from the matrix and k >= m0 + 128 from the transposed view.
@@ -754,11 +795,31 @@ extern "C" int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, con
         // W = Y T + V M2
         if ((rc = dgemm(s, BW, BW, View{Y, BW, 1}, View{Tq, BW, 1}, BW, View{Vp, BW, 1}, View{M2, BW, 1}, 1.0, 0.0, W, BW, 1, st)) != GNNGP_OK) return rc;
         // A22 -= V W^T + W V^T        B(k, j) = W[j][k] / V[j][k]; only the tiles that touch the lower triangle
-        if ((rc = dgemm(s, s, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st, 1)) != GNNGP_OK) return rc;
+        const int64_t s_next = s - BW;                      // rows of the next panel
+        if (la.on && q + 1 < p.panels && s_next > 0) {
+            // first BW columns (the next diagonal block and the next panel) ...
+            if ((rc = dgemm(s, BW, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st, 1)) != GNNGP_OK) return rc;
+            GNNGP_CUDA(cudaEventRecord(la.cols_done, st));
+            GNNGP_CUDA(cudaStreamWaitEvent(la.side, la.cols_done, 0));
+            // ... then, on the side stream, the next panel's QR and band columns
+            double *Vn = Vp + s * BW;
+            if ((rc = panel_qr(A + (r0 + BW) * lda + r0, lda, s_next, Vn, R, Tall + (q + 1) * BW * BW, ps, la.side)) != GNNGP_OK) return rc;
+            band_extract_kernel<<<BW, 128, 0, la.side>>>(A, lda, m, r0, R, 1, Bd);
+            GNNGP_LAUNCHED();
+            GNNGP_CUDA(cudaEventRecord(la.panel_done, la.side));
+            have_panel = true;
+            // ... while the main stream updates the remaining columns
+            double *A33 = A22 + BW * lda + BW;
+            const double *V2 = Vp + BW * BW, *W2 = W + BW * BW;
+            if ((rc = dgemm(s_next, s_next, BW, View{V2, BW, 1}, View{W2, 1, BW}, BW, View{W2, BW, 1}, View{V2, 1, BW}, -1.0, 1.0, A33, lda, 1, st, 1)) != GNNGP_OK) return rc;
+        } else {
+            if ((rc = dgemm(s, s, BW, View{Vp, BW, 1}, View{W, 1, BW}, BW, View{W, BW, 1}, View{Vp, 1, BW}, -1.0, 1.0, A22, lda, 1, st, 1)) != GNNGP_OK) return rc;
+        }
         // right-hand sides: rhs[:, r0:] <- rhs[:, r0:] (I - V T V^T)   (= (Q_p^T c)^T)
         if ((rc = apply_reflector(rhs, lda, C, r0, s, Vp, Tq, false, P, st)) != GNNGP_OK) return rc;
         Vp += s * BW;
     }
+    if (have_panel) GNNGP_CUDA(cudaStreamWaitEvent(st, la.panel_done, 0));
     // last block: already inside the band
     for (int64_t j0 = p.panels * BW; j0 < m; j0 += BW) {
         band_extract_kernel<<<BW, 128, 0, st>>>(A, lda, m, j0, R, 0, Bd);

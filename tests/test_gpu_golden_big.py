@@ -47,6 +47,11 @@ def test_full_size_run_matches_reference_golden(name):
                            torch.argmax(fit[best], 1).cpu().numpy(), {k: v.numpy() for k, v in model.result.items()}, sizes)
     rep["best_nugget_index_ours"] = int(torch.argmax(model.result["val"]))
     rep["best_nugget_index_reference"] = best
+    from gnngp_b200.ops import default_ops
+    rep["root_solver"] = getattr(default_ops(), "last_root_solver", None)       # "krylov" on the arxiv shape (9 094 landmarks)
+    rep["root_stats"] = {k: v for k, v in (getattr(default_ops(), "last_root_stats", None) or {}).items()} \
+        if rep["root_solver"] == "krylov" else None
+    rep["fit_solver"] = getattr(default_ops(), "last_fit_solver", None)
     print("\n%s: %s" % (name, json.dumps(rep)))
     os.makedirs("gpurun_out", exist_ok=True)
     with open(os.path.join("gpurun_out", "parity_big_%s.json" % name), "w") as fh:
