@@ -23,17 +23,26 @@ using f64::splits_for;
 
 constexpr int NB = 128;                 // Cholesky panel = largest block of potrf_inv_block
 constexpr int LDB = NB + 1;             // odd pitch: column walks hit distinct banks
-constexpr int PT = 1024;                // threads of the block kernel
+constexpr int PT = 512;                 // threads of the block kernel (128 registers each: the register-tile phases need > 64)
+constexpr int RT = PT / 32;             // its warps
 constexpr int JB = 16;                  // inner block of the one-CTA factorisation
 
 // ---------------------------------------------------------------------------------------------
-// One CTA: Cholesky factor of an nb x nb block (lower triangle of A, in place) and its inverse.
-// Factorisation: blocked right-looking in shared memory, 16 columns per step (the first version did one column per step:
-// three block barriers, a redundant sqrt / division in every warp and a rank-1 update per column — 206 us per block,
-// 31 ms of the 210 ms Krylov root, profiles/r2/call18_launches_root_summary.txt).  A non-positive pivot is
-// counted in `info` and replaced by 1 so that the kernel finishes with finite numbers (the caller discards them).
-// Inverse: column c of X = L^-1 by forward substitution, 8 lanes per column sharing each dot product; X^T lives in the
-// strict upper triangle of the same shared-memory block (free after the factorisation), its diagonal in `dinv`.
+// One CTA: Cholesky factor of an nb x nb block (lower triangle of A, in place) and its inverse, all in shared memory.
+// Factorisation, blocked right-looking, JB = 16 columns per step:
+//   (1) warp 0 factorises the 16 x 16 diagonal block in REGISTERS (lane r holds row r; pivots and multipliers travel by
+//       shuffles) while warps 1.. wait at the barrier;
+//   (2) one thread per row below solves its 16 entries by forward substitution (registers, broadcast reads of the block);
+//   (3) all threads apply the rank-16 update to the trailing lower triangle from register tiles (rows ty + 16 a,
+//       columns tx + 32 b: consecutive lanes read consecutive rows of the odd-pitch block — conflict-free — and a warp's
+//       row operand is a broadcast).
+// Inverse X = L^-1, block forward substitution: the eight 16 x 16 diagonal blocks are inverted first (one thread per
+// column, registers), then row block I = 1..7: W = L[I, 0:I] X[0:I, 0:I] with one thread per output entry (both operands
+// are contiguous along the contraction: X^T lives in the strict upper triangle of the same block, its diagonal in
+// `dinv`), and X[I, 0:I] = -X[I, I] W through shuffles inside each 16-lane group.
+// History (ncu, profiles/r2/call19_ncu_potrf_block.txt): a column-at-a-time version with an 8-lanes-per-column inverse
+// executed 634 k warp instructions for 0.35 M useful FMAs (211 us per block).
+// A non-positive pivot is counted in `info` and replaced by 1 so that the kernel finishes with finite numbers.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT, 1)
 potrf_inv_block_kernel(double *__restrict__ A, int64_t lda, int nb, double *__restrict__ Linv, int64_t ldi, int *__restrict__ info)
@@ -44,122 +53,149 @@ potrf_inv_block_kernel(double *__restrict__ A, int64_t lda, int nb, double *__re
     const int t = threadIdx.x;
     const int tx = t & 31, ty = t >> 5;
     if (t == 0) bad_s = 0;
-    for (int i = ty; i < nb; i += 32)
-        for (int j = tx; j < nb; j += 32) sm[i * LDB + j] = (j <= i) ? A[i * lda + j] : 0.0;
+    // rows / columns beyond a ragged block are padded with the identity: every 16-block below is then full
+    const int nbp = (nb + JB - 1) / JB * JB;
+    for (int i = ty; i < nbp; i += RT)
+        for (int j = tx; j < nbp; j += 32)
+            sm[i * LDB + j] = (i < nb && j <= i) ? A[i * lda + j] : ((i == j) ? 1.0 : 0.0);
     __syncthreads();
-    // blocked right-looking factorisation, JB columns at a time: (1) warp 0 factorises the JB x JB diagonal block,
-    // (2) one thread per row below it solves its JB entries by forward substitution, (3) all threads apply the rank-JB
-    // update to the trailing lower triangle from register tiles (rows ty + 32 a, columns tx + 32 b: consecutive lanes
-    // read consecutive rows of the odd-pitch block — conflict-free — and a warp's row operand is a broadcast).
-    for (int jb = 0; jb < nb; jb += JB) {
-        const int w = min(JB, nb - jb);
+    for (int jb = 0; jb < nbp; jb += JB) {
         if (ty == 0) {
-            // the JB x JB diagonal block in the registers of ONE warp: lane r holds row r, pivots and multipliers travel
-            // by shuffles (a shared-memory version spent ~800 cycles per pivot on sqrt + division + three warp barriers).
-            // Rows / columns beyond a ragged block act as an identity block.
             const int r = tx & (JB - 1);
             double a[JB];
 #pragma unroll
-            for (int c2 = 0; c2 < JB; ++c2)
-                a[c2] = (r < w && c2 < w) ? ((c2 <= r) ? sm[(jb + r) * LDB + jb + c2] : 0.0) : (c2 == r ? 1.0 : 0.0);
+            for (int c2 = 0; c2 < JB; ++c2) a[c2] = sm[(jb + r) * LDB + jb + c2];     // (the upper part is zero)
 #pragma unroll
             for (int c = 0; c < JB; ++c) {
                 const double d = __shfl_sync(0xffffffffu, a[c], c);
                 const bool ok = d > 0.0;
                 const double rs = ok ? rsqrt(d) : 1.0;
-                if (r == c) {
-                    a[c] = ok ? d * rs : 1.0;
-                    if (tx == c && c < w) {
-                        dinv[jb + c] = rs;
-                        if (!ok) bad_s = 1;
-                    }
-                } else if (r > c) {
-                    a[c] *= rs;
+                // (selects, not branches on r: a branch per unrolled c makes the compiler index a[] dynamically -> local memory)
+                const double diag = ok ? d * rs : 1.0;
+                a[c] = (r == c) ? diag : a[c] * rs;           // rows r < c hold zeros in column c
+                if (tx == c) {
+                    dinv[jb + c] = rs;
+                    if (!ok) bad_s = 1;
                 }
 #pragma unroll
-                for (int c2 = c + 1; c2 < JB; ++c2) {
-                    const double l2 = __shfl_sync(0xffffffffu, a[c], c2);
-                    if (r >= c2) a[c2] = fma(-a[c], l2, a[c2]);
+                for (int c2 = 0; c2 < JB; ++c2) {            // (constant bounds: the triangular form was not fully unrolled)
+                    if (c2 > c) {
+                        const double l2 = __shfl_sync(0xffffffffu, a[c], c2);
+                        if (r >= c2) a[c2] = fma(-a[c], l2, a[c2]);
+                    }
                 }
             }
-            if (tx < w) {
+            if (tx < JB) {
 #pragma unroll
                 for (int c2 = 0; c2 < JB; ++c2)
-                    if (c2 <= tx && c2 < w) sm[(jb + tx) * LDB + jb + c2] = a[c2];
+                    if (c2 <= tx) sm[(jb + tx) * LDB + jb + c2] = a[c2];
             }
         }
         __syncthreads();
-        const int r0 = jb + w, rem = nb - r0;                // first trailing row, trailing rows
+        const int r0 = jb + JB, rem = nbp - r0;              // first trailing row, trailing rows
         if (t < rem) {
             double x[JB];
             double *row = sm + (r0 + t) * LDB + jb;
+            const double *blk = sm + jb * LDB + jb;
 #pragma unroll
             for (int c = 0; c < JB; ++c) {
-                if (c < w) {
-                    double v = row[c];
+                double v = row[c];
 #pragma unroll
-                    for (int m = 0; m < c; ++m) v = fma(-x[m], sm[(jb + c) * LDB + jb + m], v);
-                    x[c] = v * dinv[jb + c];
-                } else {
-                    x[c] = 0.0;
-                }
+                for (int m = 0; m < JB; ++m)
+                    if (m < c) v = fma(-x[m], blk[c * LDB + m], v);
+                x[c] = v * dinv[jb + c];
             }
 #pragma unroll
-            for (int c = 0; c < JB; ++c)
-                if (c < w) row[c] = x[c];
+            for (int c = 0; c < JB; ++c) row[c] = x[c];
         }
         __syncthreads();
-        if (rem > 0) {
-            double acc[4][4];
+        // rows i = ty + RT a (warp-uniform), columns l = tx + 32 b; tile (a, b) can touch the lower triangle only when
+        // its last row reaches its first column: RT a + RT - 1 >= 32 b
+        const int na = (rem - ty + RT - 1) / RT;             // valid a for this warp (<= 0: nothing to do)
+        if (na > 0) {
+            constexpr int NA = NB / RT;
+            double acc[NA][4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-            for (int c = 0; c < w; ++c) {
-                double pi[4], pl[4];
+            const double *pi = sm + (r0 + ty) * LDB + jb;
+            const double *pl = sm + (r0 + tx) * LDB + jb;
+            const int nl = (rem - tx + 31) >> 5;             // valid b for this lane
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int i = ty + 32 * a, l = tx + 32 * a;
-                    pi[a] = (i < rem) ? sm[(r0 + i) * LDB + jb + c] : 0.0;
-                    pl[a] = (l < rem) ? sm[(r0 + l) * LDB + jb + c] : 0.0;
+            for (int c = 0; c < JB; ++c) {
+                double vl[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) vl[b] = (b < nl) ? pl[b * 32 * LDB + c] : 0.0;
+#pragma unroll
+                for (int a = 0; a < NA; ++a) {
+                    const double vi = (a < na) ? pi[a * RT * LDB + c] : 0.0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (RT * a + RT - 1 >= 32 * b) acc[a][b] = fma(vi, vl[b], acc[a][b]);
                 }
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b <= a; ++b)
-                        if (32 * a < rem) acc[a][b] = fma(pi[a], pl[b], acc[a][b]);
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
-                for (int b = 0; b <= a; ++b) {
-                    const int i = ty + 32 * a, l = tx + 32 * b;
-                    if (i < rem && l <= i) sm[(r0 + i) * LDB + r0 + l] -= acc[a][b];
+                for (int b = 0; b < 4; ++b) {
+                    const int i = ty + RT * a, l = tx + 32 * b;
+                    if (RT * a + RT - 1 >= 32 * b && i < rem && l <= i) sm[(r0 + i) * LDB + r0 + l] -= acc[a][b];
                 }
         }
         __syncthreads();
     }
-    for (int i = ty; i < nb; i += 32)
+    for (int i = ty; i < nb; i += RT)
         for (int j = tx; j <= i; j += 32) A[i * lda + j] = sm[i * LDB + j];
     if (Linv != nullptr) {
-        const int c = t >> 3, part = t & 7;
-        const bool mine = c < nb;
-        for (int i = 1; i < nb; ++i) {
-            double sum = 0.0;
-            if (mine && c < i) {
-                for (int k = c + part; k < i; k += 8) {
-                    const double xk = (k == c) ? dinv[c] : sm[c * LDB + k];
-                    sum = fma(sm[i * LDB + k], xk, sum);
-                }
+        // ---- diagonal blocks of X: thread j of block I solves column j of L[I, I] X = I  (X^T into the upper triangle)
+        if (t < nbp) {
+            const int base = t & ~(JB - 1), j = t & (JB - 1);
+            const double *blk = sm + base * LDB + base;
+            double x[JB];
+#pragma unroll
+            for (int i = 0; i < JB; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int m = 0; m < JB; ++m)
+                    if (m < i) v = fma(blk[i * LDB + m], (m >= j) ? x[m] : 0.0, v);
+                x[i] = (i == j) ? dinv[base + i] : ((i > j) ? -v * dinv[base + i] : 0.0);
             }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            if (mine && c < i && part == 0) sm[c * LDB + i] = -sum * dinv[i];
-            __syncwarp();
+            double *out = sm + (base + j) * LDB + base;
+#pragma unroll
+            for (int i = 0; i < JB; ++i)
+                if (i > j) out[i] = x[i];
         }
         __syncthreads();
-        for (int i = ty; i < nb; i += 32)
+        // ---- row blocks I = 1 ..: X[I, 0:I] = -X[I, I] (L[I, 0:I] X[0:I, 0:I])
+        const int r = t & (JB - 1);
+        for (int ib = JB; ib < nbp; ib += JB) {
+            const double *lrow = sm + (ib + r) * LDB;       // row ib + r of L
+            for (int col = t >> 4; col < ib; col += PT / JB) {
+                // w = sum_{m = col .. ib-1} L[ib + r][m] X[m][col];  X[m][col] = sm[col][m] (m > col), dinv[col] (m = col)
+                const double *xcol = sm + col * LDB;
+                double w0 = lrow[col] * dinv[col], w1 = 0.0;
+                int m = col + 1;
+                for (; m + 1 < ib; m += 2) {
+                    w0 = fma(lrow[m], xcol[m], w0);
+                    w1 = fma(lrow[m + 1], xcol[m + 1], w1);
+                }
+                if (m < ib) w0 = fma(lrow[m], xcol[m], w0);
+                const double w = w0 + w1;
+                // out[r] = -sum_{q <= r} X[ib + r][ib + q] w[q];  the w of row q sits in lane (group base + q)
+                double acc = 0.0;
+                const int gbase = tx & ~(JB - 1);
+#pragma unroll
+                for (int q = 0; q < JB; ++q) {
+                    const double wq = __shfl_sync(0xffffffffu, w, gbase + q);
+                    const double xq = (q < r) ? sm[(ib + q) * LDB + ib + r] : ((q == r) ? dinv[ib + r] : 0.0);
+                    acc = fma(xq, wq, acc);
+                }
+                sm[col * LDB + ib + r] = -acc;               // X[ib + r][col], transposed storage
+            }
+            __syncthreads();
+        }
+        for (int i = ty; i < nb; i += RT)
             for (int j = tx; j < nb; j += 32)
                 Linv[i * ldi + j] = (j < i) ? sm[j * LDB + i] : (j == i ? dinv[i] : 0.0);
     }

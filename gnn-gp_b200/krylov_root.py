@@ -163,8 +163,8 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
             _orthonormalise(ops, work, basis[:, (j + 1) * BLOCK:(j + 2) * BLOCK], info, gram, tmp)
         dim = blocks_done * BLOCK
         phases.mark("lanczos")
-        got = _rayleigh_ritz(ops, chol, basis[:, :dim], mbasis[:, :dim], info, stats, BLOCK, phases)
-        if isinstance(got, str):                                     # "breakdown"
+        got = _rayleigh_ritz(ops, chol, basis[:, :dim], mbasis[:, :dim], info, stats, BLOCK, phases, checkpoints[-1] * BLOCK)
+        if isinstance(got, str):                                     # "breakdown" / "hopeless"
             break
         if got is not None:
             result = got
@@ -178,9 +178,10 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
     return result
 
 
-def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases):
+def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases, dim_budget):
     """Project, solve the small eigenproblem, test the Ritz pairs above the clamp, assemble ``Sᵀ``.  Returns the pair of
-    factors, ``None`` (not converged at this dimension) or ``"breakdown"`` (non-positive pivot somewhere)."""
+    factors, ``None`` (not converged at this dimension), ``"breakdown"`` (non-positive pivot somewhere) or ``"hopeless"``
+    (too many eigenvalues above the clamp for the dimension budget)."""
     n, dim = basis.shape
     dev = basis.device
     f64 = torch.float64
@@ -201,7 +202,9 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases):
     if stats is not None:
         stats.setdefault("ritz_above_clamp", []).append(k)
     if k_check + block > dim:                                        # the Krylov space has not reached past the clamp yet
-        return None
+        # ... and will not within the budget when it is saturated with wanted Ritz values this early (Ritz counts are
+        # lower bounds of the true count, and convergence needs a space ~2.5x the count): hand the block back now
+        return "hopeless" if k > 0.3 * dim_budget else None
     sel = theta_host[dim - k_check:]
     y_sel = y[:, dim - k_check:]
     pitch = k_check + (k_check & 1)                                  # even row pitch: the fp64 GEMM's aligned fast path
