@@ -442,6 +442,7 @@ def run_ours(args):
     # include the operand split pre-pass
     roof_tensor = None
     tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+    tf32_sustained = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)) / 2.0   # under the power cap: a long step
 
     def tensor_entry(op_name, kernel_name, share=1.0):
         calls = [(i, ms) for i, ms in timer.calls(op_name) if i is not None]
@@ -455,7 +456,8 @@ def run_ours(args):
         return {"bound": "tensor", "kernel": "%s (%d x %d x %d, 3xTF32)" % (kernel_name, gm, gn, gk),
                 "achieved": round(useful, 1), "issued_tflops": round(3 * useful, 1), "peak": round(tf32_peak, 1),
                 "peak_source": "%s bf16 burst / 2 (TF32)" % peaks["source"], "unit": "TFLOP/s",
-                "frac": round(3 * useful / tf32_peak, 4), "ms_per_launch": round(gms, 3), "flops": share * 2.0 * gm * gn * gk,
+                "frac": round(3 * useful / tf32_peak, 4), "peak_sustained": round(tf32_sustained, 1),
+                "frac_sustained": round(3 * useful / tf32_sustained, 4), "ms_per_launch": round(gms, 3), "flops": share * 2.0 * gm * gn * gk,
                 "note": "useful flops x 3 MMAs per product (fp32-equivalent split) against the TF32 rate"}
 
     entries = [e for e in (tensor_entry("nugget_sweep", "gemm_nt_tc3_kernel<EpiSweep>"),
@@ -467,6 +469,40 @@ def run_ours(args):
         entries.sort(key=lambda e: -e["flops"])
         roof_tensor = entries[0]
         roof_tensor["others"] = [{k: e[k] for k in ("kernel", "achieved", "frac", "ms_per_launch")} for e in entries[1:]]
+
+    # ---- fp64 tensor side: the Lanczos product M V (n x 128 x n) of the Krylov Nystrom root and the rank-256 symmetric
+    # update of the band reduction, timed here in isolation (CUDA events) at the step's landmark count
+    roof_fp64 = None
+    if world == 1 and hasattr(ops, "dgemm") and info["landmarks"] >= 1024:
+        try:
+            nl = int(info["landmarks"])
+            m64 = torch.randn((nl, nl), dtype=torch.float64, device=dev)
+            v64 = torch.randn((nl, 256), dtype=torch.float64, device=dev)
+            o64 = torch.empty((nl, 128), dtype=torch.float64, device=dev)
+
+            def timed(fn, reps=5):
+                fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+            t_mv = timed(lambda: ops.dgemm(m64, v64[:, :128], out=o64))
+            t_up = timed(lambda: ops.dgemm(v64, v64.T, out=m64, alpha=-1.0, beta=1.0, lower=True))
+            fp64_peak = 40.0                                             # B200 fp64 tensor, nominal (no measured figure in MEASURED_PEAKS.json)
+            mv = 2.0 * nl * nl * 128 / (t_mv * 1e-3) / 1e12
+            up = 2.0 * (nl * nl / 2.0 + nl * 128.0) * 256 / (t_up * 1e-3) / 1e12
+            roof_fp64 = {"bound": "fp64-tensor", "kernel": "dgemm_fast_kernel (Lanczos product %d x 128 x %d)" % (nl, nl),
+                         "achieved": round(mv, 1), "peak": fp64_peak, "peak_source": "nominal B200 fp64 tensor rate (cuBLAS reaches 34 on this product)",
+                         "unit": "TFLOP/s", "frac": round(mv / fp64_peak, 4), "ms_per_launch": round(t_mv, 3),
+                         "others": [{"kernel": "dgemm_fast_kernel (lower rank-256 update %d x %d)" % (nl, nl), "achieved": round(up, 1),
+                                     "frac": round(up / fp64_peak, 4), "ms_per_launch": round(t_up, 3)}]}
+            del m64, v64, o64
+        except RuntimeError:
+            roof_fp64 = None
+        torch.cuda.empty_cache()
 
     # ---- samples of the timed run's outputs for the parity record (single GPU: Q and fit hold all rows)
     n = info["nodes"]
@@ -627,7 +663,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": round(seconds * 1e3, 3), "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
-                "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "sweep": sweep,
+                "roofline": roof, "roofline_tensor": roof_tensor, "roofline_fp64": roof_fp64, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "sweep": sweep,
                 "stages_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}}
         if args.breakdown:
             with open(args.breakdown, "w") as fh:

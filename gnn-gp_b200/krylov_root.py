@@ -110,6 +110,47 @@ def _orthonormalise(ops, w: torch.Tensor, out: torch.Tensor, info: torch.Tensor,
     ops.dgemm(tmp, linv.T, out=out)
 
 
+_SIDE_STREAMS = {}
+
+
+class _CholeskyJob(object):
+    """The Cholesky factor of M, needed only by the assembly.  It is launched on a side stream just before the
+    Rayleigh-Ritz step so that its GEMMs fill the GPU while the small projected eigenproblem (a chain of latency-bound
+    library kernels, ~27 ms at Krylov dimension 1 792) runs on the main stream; ``get`` joins the streams and returns the
+    factor, or ``None`` after a non-positive pivot."""
+
+    def __init__(self, ops, m64):
+        self.ops, self.m64, self.chol, self.info, self.side = ops, m64, None, None, None
+
+    def start(self):
+        if self.chol is not None:
+            return
+        dev = self.m64.device
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        if dev.type != "cuda" or os.environ.get("GNNGP_ROOT_OVERLAP", "1") == "0":
+            self.chol = self.m64.clone()
+            self.ops.potrf_f64(self.chol, self.info)
+            return
+        main = torch.cuda.current_stream(dev)
+        self.side = _SIDE_STREAMS.get(dev.index)
+        if self.side is None:
+            self.side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.chol = self.m64.clone()
+            self.ops.potrf_f64(self.chol, self.info)
+        self.chol.record_stream(main)
+        self.info.record_stream(self.side)
+        self.m64.record_stream(self.side)                            # (the caller may drop M before the side stream is done)
+
+    def get(self):
+        self.start()
+        if self.side is not None:
+            torch.cuda.current_stream(self.m64.device).wait_stream(self.side)
+            self.side = None
+        return self.chol if int(self.info.item()) == 0 else None
+
+
 def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
                  block: Optional[int] = None) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
     """(``Sᵀ`` as the fp32 B operand of ``E @ S`` — the role of ``(V D~)ᵀ`` in ``Pipeline._root_factors`` — and the
@@ -125,10 +166,7 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
     phases = _Phases(stats, dev)
     m64 = ops.sym_f64(kmm)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
-    # ---- Cholesky factor (a copy: the Lanczos products need M itself)
-    chol = m64.clone()
-    ops.potrf_f64(chol, info)
-    phases.mark("cholesky")
+    chol = _CholeskyJob(ops, m64)                                    # launched at the first Rayleigh-Ritz step
 
     # ---- block Lanczos with full re-orthogonalisation
     dim_max = (checkpoints[-1] + 1) * BLOCK
@@ -187,9 +225,10 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases, dim_bud
     f64 = torch.float64
     h = torch.empty((dim, dim), dtype=f64, device=dev)
     ops.dgemm(basis.T, mbasis, out=h)
-    # the one host synchronisation of the route: pivot flag + Ritz values
+    # the first host synchronisation of the route: breakdown flag of the Cholesky-QR steps
     if int(info.item()) != 0:
         return "breakdown"
+    chol.start()                                                     # side stream: overlaps the small eigenproblem
     theta, y = ops.eigh_small_f64(h)                                 # ascending
     phases.mark("projected_eigh")
     theta_host = theta.cpu()
@@ -222,6 +261,10 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases, dim_bud
     phases.mark("ritz_vectors")
     if not worst <= 1.0:
         return None
+    chol = chol.get()
+    if chol is None:
+        return "breakdown"
+    phases.mark("cholesky_wait")
     # ---- rotate the Cholesky factor into the graded basis: B = L Q_H with Q_H = [Z | Z_perp], Z = L^T V_t Theta^-1/2
     vt = ritz[:, k_check - k:]                                       # the k Ritz vectors above the clamp
     theta_t = sel[k_check - k:]
