@@ -902,3 +902,47 @@ extern "C" int gnngp_qr_rotate_f64(double *x, int64_t ldx, int64_t rows, double 
     }
     return GNNGP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// (band(H) + shifts[g] I) x = rhs for every shift, H symmetric [dim x dim] fp64 of which the band |i - j| <= 128 of the
+// lower triangle is used (block-tridiagonal projected matrices of a block Lanczos process with blocks <= 64), by the
+// banded Cholesky + substitution kernel of the band fit, one CTA per shift.  rhs_t: [C x dim] vectors as rows;
+// sol_t: [(G*C) x dim].  info counts shifts with a non-positive pivot.
+// ---------------------------------------------------------------------------------------------
+namespace gnngp {
+namespace bandfit {
+__global__ void band_from_dense_kernel(const double *__restrict__ H, int64_t ldh, int64_t dim, double *__restrict__ Bd)
+{
+    const int64_t j = blockIdx.x;
+    for (int k = threadIdx.x; k <= BW; k += blockDim.x) Bd[j * (BW + 1) + k] = (j + k < dim) ? H[(j + k) * ldh + j] : 0.0;
+}
+}  // namespace bandfit
+}  // namespace gnngp
+
+extern "C" size_t gnngp_band_solve_workspace_bytes(int64_t dim, int64_t C, int64_t G)
+{
+    if (dim <= 0 || C <= 0 || G <= 0) return 256;
+    return (size_t)dim * (BW + 1) * 8 + (size_t)G * dim * (BW + 1) * 8 + 1024;
+}
+
+extern "C" int gnngp_band_solve_f64(const double *h, int64_t ldh, int64_t dim, const double *rhs_t, int64_t ldr, int64_t C,
+                                    const double *shifts, int64_t G, double *sol_t, int64_t lds, int32_t *info, void *workspace,
+                                    size_t workspace_bytes, gnngp_stream_t stream)
+{
+    GNNGP_REQUIRE(h && rhs_t && shifts && sol_t && info && dim > 0 && C > 0 && G > 0 && ldh >= dim && ldr >= dim && lds >= dim,
+                  "band_solve: bad arguments");
+    GNNGP_REQUIRE(C <= RHS_MAX, "band_solve: at most %d right-hand sides per shift (got %lld)", RHS_MAX, (long long)C);
+    GNNGP_REQUIRE(workspace && aligned(workspace, 256) && workspace_bytes >= gnngp_band_solve_workspace_bytes(dim, C, G),
+                  "band_solve: workspace must be 256-byte aligned and hold gnngp_band_solve_workspace_bytes(dim, C, G)");
+    cudaStream_t st = as_stream(stream);
+    double *Bd = reinterpret_cast<double *>(workspace);
+    double *Lg = Bd + ((size_t)dim * (BW + 1) + 31) / 32 * 32;
+    GNNGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    band_from_dense_kernel<<<(unsigned)dim, 128, 0, st>>>(h, ldh, dim, Bd);
+    GNNGP_LAUNCHED();
+    const size_t smem = (size_t)(SLOTS * RHS_LD + 2 * CH * (WIN + RHS_MAX) + WIN + RHS_MAX + WIN) * sizeof(double);
+    GNNGP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void *>(band_cholesky_solve_kernel), (int)smem));
+    band_cholesky_solve_kernel<<<(unsigned)G, SOLVE_THREADS, smem, st>>>(Bd, dim, shifts, rhs_t, ldr, (int)C, Lg, sol_t, lds, info);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}

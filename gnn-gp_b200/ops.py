@@ -587,6 +587,35 @@ class CudaOps(object):
                       self._stream())
         return X
 
+    def krylov_root(self, kmm: torch.Tensor, stats: Optional[dict] = None):
+        """The Nystrom root of a landmark block by ``krylov_root.root_factors`` (an operator so that it shows up as ONE
+        stage in the bench's timing table); ``None`` when the route hands the block back."""
+        from . import krylov_root as route
+        return route.root_factors(self, kmm, stats)
+
+    def krylov_fit(self, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Tensor, stats: Optional[dict] = None):
+        """All nuggets' coefficient blocks by ``krylov_fit.coefficients`` (one timed stage); ``None`` = not converged."""
+        from . import krylov_fit as route
+        return route.coefficients(self, gram, qty_t, shifts, stats)
+
+    def band_solve(self, H: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.Tensor):
+        """``(band(H) + shifts[g] I) x = rhs`` for every shift (the band |i - j| <= 128 of the lower triangle of the fp64
+        matrix ``H`` is used): fp64 [(G*C) x dim] solutions (vectors as rows) and a device int32 counting non-positive
+        pivots.  ``rhs_t`` fp64 [C x dim], C <= 48."""
+        self._f64_view(H, "H"), self._f64_view(rhs_t, "rhs_t")
+        dim, c, g = H.shape[0], rhs_t.shape[0], shifts.numel()
+        if H.shape[1] != dim or rhs_t.shape[1] != dim or H.stride(1) != 1 or rhs_t.stride(1) != 1:
+            raise RuntimeError("band_solve: H [dim x dim] and rhs_t [C x dim] row-major expected")
+        shifts = shifts.to(torch.float64).contiguous()
+        sol = torch.empty((g * c, dim), dtype=torch.float64, device=H.device)
+        info = torch.zeros(1, dtype=torch.int32, device=H.device)
+        need = self.lib.query("gnngp_band_solve_workspace_bytes", dim, c, g)
+        ws = self.workspace(need + 256, H.device, "band_solve")
+        wptr = (ws.data_ptr() + 255) // 256 * 256
+        self.lib.call("gnngp_band_solve_f64", H.data_ptr(), H.stride(0), dim, rhs_t.data_ptr(), rhs_t.stride(0), c,
+                      shifts.data_ptr(), g, sol.data_ptr(), dim, info.data_ptr(), wptr, need, self._stream())
+        return sol, info
+
     def eigh_small_f64(self, H: torch.Tensor):
         """Rayleigh-Ritz step of the Krylov root: eigendecomposition of the SMALL projected matrix (dimension ~0.11 n;
         cuSOLVER through torch, 1/200 of the flops of the eigendecomposition it replaces)."""

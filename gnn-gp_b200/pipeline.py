@@ -19,7 +19,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import krylov_root
+from . import krylov_fit, krylov_root
 
 
 class LocalComm(object):
@@ -104,8 +104,10 @@ class Pipeline(object):
         ops = self.ops
         if krylov_root.wanted(kmm.shape[0], ops):
             stats = {}
-            got = krylov_root.root_factors(ops, kmm, stats)
+            route = getattr(ops, "krylov_root", None)                 # (the CUDA operator set wraps it as one timed stage)
+            got = route(kmm, stats) if route is not None else krylov_root.root_factors(ops, kmm, stats)
             self.last_root_stats = ops.last_root_stats = stats
+            got = got if self._all_ranks(got is not None, kmm.device) else None
             if got is not None:
                 self.last_root_solver = ops.last_root_solver = "krylov"
                 return got
@@ -115,6 +117,17 @@ class Pipeline(object):
         w_t = ops.scale_cols(evecs, inv, transpose=True)      # (V * D^-1/2~)^T, the B operand of E @ (V D~)
         v_root = ops.scale_cols(evecs, root)                   # V * sqrt(D+): the landmark rows of the factor
         return w_t, v_root
+
+    def _all_ranks(self, ok: bool, device) -> bool:
+        """True when ``ok`` holds on EVERY rank.  The iterative routes (Krylov root, Krylov fit) run replicated on
+        identical inputs, but their kernels sum with atomics, so a convergence test at a knife edge could come out
+        differently on two ranks — and a rank that falls back alone would use another basis (root) or enter a
+        collective the others skip (fit).  One small all-reduce makes the decision common."""
+        if self.comm.world == 1:
+            return ok
+        flag = torch.tensor([1.0 if ok else 0.0], device=device)
+        self.comm.all_reduce_sum(flag)
+        return int(round(float(flag))) == self.comm.world
 
     def _mark(self, ref: torch.Tensor):
         """Event on the current stream (None off-GPU)."""
@@ -509,6 +522,11 @@ class Pipeline(object):
             comm.all_reduce_sum(gram)
             comm.all_reduce_sum(qty_t)
             comm.all_reduce_sum(scale)
+        if krylov_fit.wanted(gram.shape[0], qty_t.shape[0], ops):
+            fitted = self._fit_by_krylov(q, gram, qty_t, scale, nugget, trailing)
+            if fitted is not None:
+                self.last_fit_solver = self.ops.last_fit_solver = "krylov"
+                return fitted
         solver = self._fit_solver(gram.shape[0], nugget.numel(), qty_t.shape[0])
         if solver == "cholesky":
             fitted = self._fit_by_shifted_solves(q, gram, qty_t, scale, nugget, trailing)
@@ -524,6 +542,25 @@ class Pipeline(object):
         evals, evecs = ops.eigh(gram)
         proj_t = ops.gemm_nt(qty_t, ops.transpose(evecs))             # (V^T Q_b^T y_b)^T  [C x m]
         return self._sweep(q, evals, evecs, proj_t, scale, nugget, trailing)
+
+    def _fit_by_krylov(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
+                       nugget: torch.Tensor, trailing):
+        """All nuggets' coefficient blocks from ONE block Lanczos process on the Gram matrix started from ``Q_bᵀy_b``
+        (``krylov_fit``: Krylov spaces are shift-invariant), then the same sweep contraction.  ``None`` when the
+        residual test of the smallest nugget is not met within the step budget — the caller then takes a direct route."""
+        ops = self.ops
+        g, c = nugget.numel(), qty_t.shape[0]
+        shifts = (nugget.to(torch.float64) * scale.to(torch.float64)).contiguous()
+        stats = {}
+        route = getattr(ops, "krylov_fit", None)
+        coeff_t = route(gram, qty_t, shifts, stats) if route is not None else krylov_fit.coefficients(ops, gram, qty_t, shifts, stats)
+        self.last_fit_stats = ops.last_fit_stats = stats
+        if not self._all_ranks(coeff_t is not None, gram.device):
+            return None
+        y_t, basis_t = coeff_t                                        # X_g = basis_t^T y_g: contract Q with the basis first
+        fitted = ops.nugget_sweep(ops.gemm_nt(q, basis_t), y_t, g, c)
+        fitted = fitted.reshape((g, q.shape[0]) + tuple(trailing))
+        return fitted[0] if g == 1 else fitted
 
     def _fit_by_band_reduction(self, q: torch.Tensor, gram: torch.Tensor, qty_t: torch.Tensor, scale: torch.Tensor,
                                nugget: torch.Tensor, trailing):

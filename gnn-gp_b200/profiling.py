@@ -13,7 +13,8 @@ import torch
 
 TIMED = ("csr_from_coo", "spmm", "spmm_panels", "panels_from_peers", "gemm_nt", "syrk", "restrict_columns", "gram_arccos", "initial_kernel", "nugget_coeff", "nugget_sweep", "row_norms",
          "gather_rows", "scatter_rows", "gather_rows_t", "gather_cols", "affine", "eigh", "nystrom_spectrum",
-         "scale_cols", "arccos_dense", "onehot_t", "argmax_count", "sqerr_sum", "mean", "fill_col", "shifted_solves", "band_fit")
+         "scale_cols", "arccos_dense", "onehot_t", "argmax_count", "sqerr_sum", "mean", "fill_col", "shifted_solves", "band_fit",
+         "krylov_root", "krylov_fit")
 
 
 class OpTimer(object):

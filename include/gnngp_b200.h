@@ -237,7 +237,14 @@ int gnngp_band_fit_f64(const float *gram, int64_t ldg, int64_t m, const float *r
  *   qr_rotate_f64        x[rows x n] <- x Q_H with Q_H the orthogonal factor of the Householder QR of z [n x kp] (kp a
  *                        multiple of 128, z overwritten): the leading columns of x Q_H are +-(x z_j) for orthonormal z_j,
  *                        the others x times an orthonormal basis of the complement (csrc/bandfit.cu panel kernels)
+ *   band_solve_f64       (band(h) + shifts[g] I) x = rhs for every shift: h symmetric [dim x dim], the band |i-j| <= 128 of
+ *                        its lower triangle is used (projected block-tridiagonal matrices); rhs_t [C x dim] vectors as rows,
+ *                        sol_t [(G*C) x dim]; one CTA per shift (the band fit's banded Cholesky kernel); C <= 48
  * No host synchronisation in any of them. */
+size_t gnngp_band_solve_workspace_bytes(int64_t dim, int64_t C, int64_t G);
+int gnngp_band_solve_f64(const double *h, int64_t ldh, int64_t dim, const double *rhs_t, int64_t ldr, int64_t C,
+                         const double *shifts, int64_t G, double *sol_t, int64_t lds, int32_t *info, void *workspace,
+                         size_t workspace_bytes, gnngp_stream_t stream);
 size_t gnngp_qr_rotate_workspace_bytes(int64_t rows, int64_t n, int64_t kp);
 int gnngp_qr_rotate_f64(double *x, int64_t ldx, int64_t rows, double *z, int64_t ldz, int64_t n, int64_t kp,
                         void *workspace, size_t workspace_bytes, gnngp_stream_t stream);

@@ -164,6 +164,20 @@ class StubOps(object):
         X.copy_(X @ q)
         return X
 
+    def band_solve(self, H, rhs_t, shifts):
+        dim, c = H.shape[0], rhs_t.shape[0]
+        low = torch.tril(H)
+        sym = low + torch.tril(low, -1).T
+        i = torch.arange(dim)
+        sym = torch.where((i.view(-1, 1) - i.view(1, -1)).abs() <= 128, sym, torch.zeros_like(sym))
+        out = torch.empty((int(shifts.numel()) * c, dim), dtype=torch.float64)
+        bad = torch.zeros(1, dtype=torch.int32)
+        for g in range(int(shifts.numel())):
+            factor, info = torch.linalg.cholesky_ex(sym + shifts[g] * torch.eye(dim, dtype=torch.float64))
+            bad += (info != 0).to(torch.int32)
+            out[g * c:(g + 1) * c] = torch.cholesky_solve(rhs_t.T.contiguous(), factor).T
+        return out, bad
+
     def eigh_small_f64(self, H):
         return torch.linalg.eigh(H)
 

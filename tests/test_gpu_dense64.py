@@ -183,3 +183,51 @@ def test_krylov_root_hands_back_what_it_cannot_do(ops):
     assert krylov_root.root_factors(ops, bad, block=32) is None
     stats = {}
     assert krylov_root.root_factors(ops, _block(1500, 1200, gap=0.9), stats, block=32) is None and not stats["converged"]
+
+
+@pytest.mark.parametrize("dim,half,c,g", [(700, 81, 41, 5), (129, 128, 3, 2), (2400, 95, 48, 101), (50, 20, 7, 3)])
+def test_band_solve_against_dense_solves(ops, dim, half, c, g):
+    """(band(H) + shift I) x = rhs for every shift: block-tridiagonal-like SPD matrices, entries beyond the band ignored."""
+    gen = torch.Generator(device=DEV).manual_seed(dim + half)
+    a = torch.randn(dim, dim, device=DEV, dtype=torch.float64, generator=gen)
+    i = torch.arange(dim, device=DEV)
+    band = (i.view(-1, 1) - i.view(1, -1)).abs() <= half
+    h = torch.where(band, (a + a.T) / 2, torch.zeros_like(a)) + (2.0 * half) * torch.eye(dim, device=DEV, dtype=torch.float64)
+    noisy = h + torch.where(band, torch.zeros_like(a), torch.full_like(a, 3.0))       # beyond |i-j| <= 128 nothing is read
+    far = (i.view(-1, 1) - i.view(1, -1)).abs() > 128
+    noisy = torch.where(far, noisy, h)
+    rhs_t = torch.randn(c, dim, device=DEV, dtype=torch.float64, generator=gen)
+    shifts = torch.logspace(-2, 1, g, device=DEV, dtype=torch.float64)
+    sol, info = ops.band_solve(noisy, rhs_t, shifts)
+    assert int(info) == 0
+    eye = torch.eye(dim, device=DEV, dtype=torch.float64)
+    for k in range(g):
+        want = torch.linalg.solve(h + shifts[k] * eye, rhs_t.T).T
+        assert rel(sol[k * c:(k + 1) * c], want) < 1e-11, (dim, k)
+
+
+def test_krylov_fit_against_dense_solves(ops):
+    """The block-Lanczos posterior solve (krylov_fit.py) through the C ABI on a Gram matrix with the benchmark's spectrum
+    shape: every nugget's coefficient block against a dense fp64 solve."""
+    from gnngp_b200 import krylov_fit
+    m, c, outliers = 4200, 41, 160
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    q, _ = torch.linalg.qr(torch.randn(m, m, device=DEV, dtype=torch.float64, generator=gen))
+    lam = torch.cat([torch.empty(m - outliers, device=DEV, dtype=torch.float64).uniform_(2e-8, 2e-7, generator=gen),
+                     torch.exp(torch.empty(outliers, device=DEV, dtype=torch.float64).uniform_(-11.5, 0.0, generator=gen))]) * 5e4
+    g64 = (q * lam) @ q.T
+    gram = ((g64 + g64.T) / 2).float()
+    qty_t = (g64 @ torch.randn(m, c, device=DEV, dtype=torch.float64, generator=gen)).float().T.contiguous()
+    d = float(torch.diagonal(gram).double().mean())
+    shifts = torch.logspace(-3, 1, 101, device=DEV, dtype=torch.float64) * d
+    stats = {}
+    got = krylov_fit.coefficients(ops, gram, qty_t, shifts, stats)
+    assert got is not None and stats["converged"], stats
+    y_t, basis_t = got
+    got = y_t.double() @ basis_t.double()                              # [(G*C) x m]
+    sym = torch.tril(gram).double()
+    sym = sym + torch.tril(sym, -1).T
+    eye = torch.eye(m, device=DEV, dtype=torch.float64)
+    for k in (0, 17, 50, 100):
+        want = torch.linalg.solve(sym + shifts[k] * eye, qty_t.double().T).T
+        assert rel(got[k * c:(k + 1) * c], want) < 2e-6, (k, stats)

@@ -85,6 +85,16 @@ def test_krylov_root_route_matches_reference_golden(name, monkeypatch):
     assert default_ops().last_root_solver in ("krylov", "eigh")
 
 
+@pytest.mark.parametrize("name", ["small-GCN-nys4-L2", "small-SAGE-nys4-L4"])
+def test_krylov_fit_route_matches_reference_golden(name, monkeypatch):
+    """The block-Lanczos posterior solve forced on one GPU (krylov_fit.py; csrc/dense64.cu, band_solve): golden check."""
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "krylov")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    out, _ = run_public_api(case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+
+
 @pytest.mark.parametrize("name", ["small-GCN-nys4-L2", "tinyreg-GIN-nys1-L3", "pubmed-GCN-nys4-L2", "chameleon-SAGE-nys1-L2"])
 def test_nugget_parallel_fit_matches_reference_golden(name, monkeypatch):
     """The sharded mode's fit route (fp64 potrf per nugget + the batched substitution kernel) forced on one

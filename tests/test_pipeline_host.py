@@ -62,6 +62,19 @@ def test_band_reduction_fit_route_matches_reference(name, monkeypatch):
     runner.check_against_golden(name, out, masks)
 
 
+@pytest.mark.parametrize("name", ["small-GCN-nys4-L2", "small-SAGE-nys4-L4"])
+def test_krylov_fit_route_matches_reference(name, monkeypatch):
+    """The block-Lanczos posterior solve (pipeline._fit_by_krylov / krylov_fit.py; factored coefficients, sweep over the
+    Krylov dimension) forced on the 176-landmark cases: golden check, whether it converges or hands back."""
+    monkeypatch.setenv("GNNGP_FIT_SOLVER", "krylov")
+    case = cases.CASES[name]
+    data, masks, nugget = cases.build_inputs(case)
+    ops = StubOps()
+    out = runner.run_pipeline(ops, case, data, masks, nugget)
+    runner.check_against_golden(name, out, masks)
+    assert getattr(ops, "last_fit_solver", None) in ("krylov", "eigh", "band")
+
+
 def test_fit_solver_policy(monkeypatch):
     from gnngp_b200.pipeline import Pipeline
 

@@ -55,6 +55,15 @@ for m, nt in ((3053, 40000), (6138, 40000), (15405, 40000)):
         return ops.gemm_nt(c, v)
     ms_eig, coeff_e = timeit(eigen_route)
     rec = {"band_fit_ms": round(ms_band, 2), "eigen_route_ms": round(ms_eig, 2), "info": int(info)}
+    kstats = {}
+    ms_kry, coeff_k = timeit(lambda: ops.krylov_fit(gram, qty_t, shifts, kstats))
+    rec["krylov_fit_ms"] = round(ms_kry, 2)
+    rec["krylov_fit"] = {k: v for k, v in kstats.items()}
+    if coeff_k is not None:
+        y_t, basis_t = coeff_k
+        for gi in (0, 50, 100):
+            a, b = y_t[gi * 41:(gi + 1) * 41].double() @ basis_t.double(), coeff[gi * 41:(gi + 1) * 41].double()
+            rec["krylov_vs_band_rel_nugget_%d" % gi] = float((a - b).norm() / b.norm())
     for gi in (0, 25, 50, 100):
         a, b = coeff[gi * 41:(gi + 1) * 41].double(), coeff_e[gi * 41:(gi + 1) * 41].double()
         rec["rel_diff_nugget_%d" % gi] = float((a - b).norm() / b.norm())
