@@ -431,6 +431,7 @@ def run_ours(args):
     table = timer.summary()
     spmm_calls = timer.calls("spmm") + timer.calls("spmm_panels")
     fit_solver = getattr(ops, "last_fit_solver", None) or "eigh"
+    fit_stats = dict(getattr(ops, "last_fit_stats", None) or {}) if fit_solver == "krylov" or getattr(ops, "last_fit_stats", None) else None
     root_solver = {"solver": getattr(ops, "last_root_solver", None) or "eigh"}
     root_solver.update({k: v for k, v in (getattr(ops, "last_root_stats", None) or {}).items() if k != "phase_ms"})
     best = {k: float(summary[k]) for k in ("train", "val", "test", "nugget")}
@@ -656,7 +657,7 @@ def run_ours(args):
         config = {"workload": workload_name(args), "graph": info,
                   "l2": "inputs larger than L2 (adjacency %.2f GB, factor %.2f GB)" % (info["nnz"] * 8 / 1e9, info["nodes"] * (info["landmarks"] + 1) * 4 / 1e9),
                   "parallelism": "row-sharded x%d" % world if world > 1 else "single GPU",
-                  "fit_solver": fit_solver, "root_solver": root_solver, "best": best, "setup_s": round(setup_s, 1),
+                  "fit_solver": fit_solver, "fit_solver_stats": fit_stats, "root_solver": root_solver, "best": best, "setup_s": round(setup_s, 1),
                   "parity_vs_reference": ({k: headline_parity[k] for k in ("qqT_rel", "fit_rel", "argmax_flips", "ok", "source")}
                                           | {"cases": parity}) if headline_parity else None}
         line = {"metric": METRIC, "value": round(seconds, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps,

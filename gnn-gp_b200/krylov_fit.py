@@ -32,7 +32,7 @@ RESIDUAL_TOL = 1e-10
 FIRST_CHECK = 20                  # Lanczos steps before the first residual test
 DECADES_PER_STEP = 0.35           # assumed convergence rate when scheduling the next test (measured: ~0.5)
 MAX_STEPS = 72                    # ... and the Krylov dimension never passes MAX_DIM_FRACTION of m
-MAX_DIM_FRACTION = 0.3
+MAX_DIM_FRACTION = 0.45
 
 
 def wanted(m: int, n_targets: int, ops) -> bool:
