@@ -23,6 +23,9 @@ def _free_port():
 
 def _worker(rank, world, port, name, out_dir, solver="auto"):
     os.environ["GNNGP_FIT_SOLVER"] = solver
+    if solver == "krylov":                                   # both Krylov routes, with a small Lanczos block for the root
+        os.environ["GNNGP_ROOT_SOLVER"] = "krylov"
+        os.environ["GNNGP_ROOT_BLOCK"] = "16"
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
     import cases
@@ -54,7 +57,9 @@ def _worker(rank, world, port, name, out_dir, solver="auto"):
                                                (3, "tiny-GCN2-nys2-L2", "auto"), (2, "tinyreg-GIN-nys1-L3", "auto"),
                                                (2, "tiny-GCN-nys8-L2", "auto"), (2, "tiny-GCN-nys2-arccos", "auto"),
                                                # nugget-parallel fit: every rank solves its share of the nugget grid
-                                               (3, "tiny-GCN-nys2-L3", "cholesky"), (2, "tinyreg-GIN-nys1-L3", "cholesky")])
+                                               (3, "tiny-GCN-nys2-L3", "cholesky"), (2, "tinyreg-GIN-nys1-L3", "cholesky"),
+                                               # replicated Krylov root / Krylov fit with the common convergence decision
+                                               (2, "small-GCN-nys4-L2", "krylov"), (3, "small-SAGE-nys4-L4", "krylov")])
 def test_sharded_matches_single_rank(tmp_path, world, name, solver):
     import cases
     import runner
