@@ -23,7 +23,7 @@ from typing import Optional
 
 import torch
 
-from .krylov_root import _orthonormalise
+from .krylov_root import RowSplit, _orthonormalise
 
 # Relative residual of the smallest nugget's solution at which the process stops.  The shifted systems are
 # ill-conditioned (condition ~1e4 after the outliers are captured): on the benchmark's Gram matrix a residual of 5e-7
@@ -47,7 +47,7 @@ def wanted(m: int, n_targets: int, ops) -> bool:
 
 
 def coefficients(ops, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Tensor,
-                 stats: Optional[dict] = None) -> Optional[torch.Tensor]:
+                 stats: Optional[dict] = None, comm=None) -> Optional[torch.Tensor]:
     """The solutions in FACTORED form ``(y_t, basis_t)``: fp32 ``y_t`` [(G*C) x dim] and ``basis_t`` [dim x m] with
     ``((gram + shifts[g] I)⁻¹ rhs)[:, c] = basis_tᵀ y_t[g*C + c]`` — so ``fitted = (Q basis_tᵀ) y_tᵀ`` — or ``None`` (no
     convergence / breakdown: use the direct route).  ``gram``: fp32 [m x m], lower triangle read;
@@ -57,6 +57,7 @@ def coefficients(ops, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Ten
     dev = gram.device
     f64 = torch.float64
     g64 = ops.sym_f64(gram)
+    split = RowSplit(ops, m, comm)                                   # sharded mode: the products' rows are divided over the ranks
     b = qty_t.to(f64).T.contiguous()                                 # [m x C]
     b_norm = torch.linalg.norm(b)
     max_steps = max(FIRST_CHECK, min(MAX_STEPS, int(MAX_DIM_FRACTION * m) // c))
@@ -64,16 +65,17 @@ def coefficients(ops, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Ten
     dim_max += dim_max & 1                                           # even pitch: the fp64 GEMM's aligned fast path
     basis = torch.empty((m, dim_max), dtype=f64, device=dev)
     gbasis = torch.empty((m, dim_max), dtype=f64, device=dev)
-    work = torch.empty((m, c), dtype=f64, device=dev)
-    tmp = torch.empty((m, c), dtype=f64, device=dev)
-    gram_c = torch.empty((c, c), dtype=f64, device=dev)
-    coef = torch.empty((dim_max, c), dtype=f64, device=dev)
+    cp = c + (c & 1)                                                 # even pitches everywhere (aligned GEMM fast path)
+    work = torch.empty((m, cp), dtype=f64, device=dev)[:, :c]
+    tmp = torch.empty((m, cp), dtype=f64, device=dev)[:, :c]
+    gram_c = torch.empty((c, cp), dtype=f64, device=dev)[:, :c]
+    coef = torch.empty((dim_max, cp), dtype=f64, device=dev)[:, :c]
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     work.copy_(b)
     _orthonormalise(ops, work, basis[:, :c], info, gram_c, tmp)
     rhs_k = torch.zeros((c, dim_max), dtype=f64, device=dev)        # (K^T B)^T: only the first block is non-zero
     ops.dgemm(b.T, basis[:, :c], out=rhs_k[:, :c])
-    x0 = torch.empty((m, c), dtype=f64, device=dev)
+    x0 = torch.empty((m, cp), dtype=f64, device=dev)[:, :c]
     i0 = int(torch.argmin(shifts))                                   # the smallest nugget converges last
     shift0 = shifts[i0:i0 + 1].to(f64)
     result = None
@@ -82,7 +84,7 @@ def coefficients(ops, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Ten
     for j in range(max_steps):
         vj = basis[:, j * c:(j + 1) * c]
         gv = gbasis[:, j * c:(j + 1) * c]
-        ops.dgemm(g64, vj, out=gv)
+        split.matmul(g64, vj, gv)
         steps = j + 1
         if steps == next_check or steps == max_steps:
             dim = steps * c

@@ -110,6 +110,58 @@ def _orthonormalise(ops, w: torch.Tensor, out: torch.Tensor, info: torch.Tensor,
     ops.dgemm(tmp, linv.T, out=out)
 
 
+class RowSplit(object):
+    """The replicated Krylov routes in sharded mode: products ``M @ V`` (and the rotation of the Cholesky factor) are
+    independent across rows of ``M``, so rank r computes rows [r * per, (r + 1) * per) and one all-gather of the equal-sized
+    row blocks hands every rank the whole result — the matrices themselves stay replicated (they come out of
+    all-reduces), only the GEMM work is divided.  ``comm`` needs ``world``, ``rank`` and ``all_gather_equal``; without it
+    (single GPU) every call is the plain local product."""
+
+    def __init__(self, ops, n: int, comm=None):
+        self.ops, self.n = ops, n
+        self.comm = comm if (comm is not None and getattr(comm, "world", 1) > 1 and hasattr(comm, "all_gather_equal")) else None
+        if self.comm is not None:
+            world = self.comm.world
+            self.per = -(-n // world)
+            self.per += self.per & 1                                  # even: keeps the row blocks 16-byte aligned
+            self.r0 = min(n, self.comm.rank * self.per)
+            self.r1 = min(n, self.r0 + self.per)
+            self._bufs = {}
+
+    def _buffers(self, cols: int, like: torch.Tensor):
+        hit = self._bufs.get(cols)
+        if hit is None:
+            piece = torch.zeros((self.per, cols), dtype=like.dtype, device=like.device)
+            full = torch.empty((self.comm.world * self.per, cols), dtype=like.dtype, device=like.device)
+            hit = self._bufs[cols] = (piece, full)
+        return hit
+
+    def matmul(self, m: torch.Tensor, v: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """``out = m @ v`` ([n x n] @ [n x c])."""
+        if self.comm is None:
+            return self.ops.dgemm(m, v, out=out)
+        piece, full = self._buffers(v.shape[1], m)
+        if self.r1 > self.r0:
+            self.ops.dgemm(m[self.r0:self.r1], v, out=piece[:self.r1 - self.r0])
+        self.comm.all_gather_equal(piece, full)
+        out.copy_(full[:self.n])
+        return out
+
+    def rotate(self, x: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        """``x <- x Q_H`` (``ops.qr_rotate``): the Householder QR of ``z`` is replicated, the reflectors are applied to
+        this rank's rows of ``x`` only."""
+        if self.comm is None or x.shape[0] != self.n:
+            return self.ops.qr_rotate(x, z)
+        piece, full = self._buffers(x.shape[1], x)
+        rows = self.r1 - self.r0
+        if rows > 0:
+            piece[:rows].copy_(x[self.r0:self.r1])
+            self.ops.qr_rotate(piece[:rows], z)
+        self.comm.all_gather_equal(piece, full)
+        x.copy_(full[:self.n])
+        return x
+
+
 _SIDE_STREAMS = {}
 
 
@@ -122,13 +174,19 @@ class _CholeskyJob(object):
     def __init__(self, ops, m64):
         self.ops, self.m64, self.chol, self.info, self.side = ops, m64, None, None, None
 
+    def _copy(self):
+        n = self.m64.shape[0]
+        out = torch.empty((n, n + (n & 1)), dtype=self.m64.dtype, device=self.m64.device)[:, :n]   # even pitch, like M
+        out.copy_(self.m64)
+        return out
+
     def start(self):
         if self.chol is not None:
             return
         dev = self.m64.device
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         if dev.type != "cuda" or os.environ.get("GNNGP_ROOT_OVERLAP", "1") == "0":
-            self.chol = self.m64.clone()
+            self.chol = self._copy()
             self.ops.potrf_f64(self.chol, self.info)
             return
         main = torch.cuda.current_stream(dev)
@@ -137,7 +195,7 @@ class _CholeskyJob(object):
             self.side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            self.chol = self.m64.clone()
+            self.chol = self._copy()
             self.ops.potrf_f64(self.chol, self.info)
         self.chol.record_stream(main)
         self.info.record_stream(self.side)
@@ -151,11 +209,13 @@ class _CholeskyJob(object):
         return self.chol if int(self.info.item()) == 0 else None
 
 
-def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
-                 block: Optional[int] = None) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None, block: Optional[int] = None,
+                 comm=None) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
     """(``Sᵀ`` as the fp32 B operand of ``E @ S`` — the role of ``(V D~)ᵀ`` in ``Pipeline._root_factors`` — and the
     fp32 landmark rows ``L``), or ``None`` when the route does not apply to this block (the caller then runs ``eigh``).
-    ``kmm``: fp32 [n x n] landmark block, lower triangle read.  ``block`` (<= 128) is the Lanczos block size."""
+    ``kmm``: fp32 [n x n] landmark block, lower triangle read.  ``block`` (<= 128) is the Lanczos block size.  ``comm``
+    (sharded mode, the block replicated on every rank): the GEMM work of the products and of the rotation is divided
+    over the ranks (``RowSplit``)."""
     n = kmm.shape[0]
     dev = kmm.device
     BLOCK = int(block if block is not None else os.environ.get("GNNGP_ROOT_BLOCK", DEFAULT_BLOCK))   # <= 128 (tests: 32)
@@ -167,6 +227,7 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
     m64 = ops.sym_f64(kmm)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     chol = _CholeskyJob(ops, m64)                                    # launched at the first Rayleigh-Ritz step
+    split = RowSplit(ops, n, comm)
 
     # ---- block Lanczos with full re-orthogonalisation
     dim_max = (checkpoints[-1] + 1) * BLOCK
@@ -188,7 +249,7 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
             j = blocks_done
             vj = basis[:, j * BLOCK:(j + 1) * BLOCK]
             mv = mbasis[:, j * BLOCK:(j + 1) * BLOCK]
-            ops.dgemm(m64, vj, out=mv)
+            split.matmul(m64, vj, mv)
             blocks_done += 1
             if blocks_done == target and target == checkpoints[-1]:
                 break                                                # the last block is only needed for the projection
@@ -201,7 +262,7 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
             _orthonormalise(ops, work, basis[:, (j + 1) * BLOCK:(j + 2) * BLOCK], info, gram, tmp)
         dim = blocks_done * BLOCK
         phases.mark("lanczos")
-        got = _rayleigh_ritz(ops, chol, basis[:, :dim], mbasis[:, :dim], info, stats, BLOCK, phases, checkpoints[-1] * BLOCK)
+        got = _rayleigh_ritz(ops, chol, basis[:, :dim], mbasis[:, :dim], info, stats, BLOCK, phases, checkpoints[-1] * BLOCK, split)
         if isinstance(got, str):                                     # "breakdown" / "hopeless"
             break
         if got is not None:
@@ -216,7 +277,7 @@ def root_factors(ops, kmm: torch.Tensor, stats: Optional[dict] = None,
     return result
 
 
-def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases, dim_budget):
+def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases, dim_budget, split):
     """Project, solve the small eigenproblem, test the Ritz pairs above the clamp, assemble ``Sᵀ``.  Returns the pair of
     factors, ``None`` (not converged at this dimension), ``"breakdown"`` (non-positive pivot somewhere) or ``"hopeless"``
     (too many eigenvalues above the clamp for the dimension budget)."""
@@ -284,7 +345,7 @@ def _rayleigh_ritz(ops, chol, basis, mbasis, info, stats, block, phases, dim_bud
         vs = torch.empty((n, k + (k & 1)), dtype=f64, device=dev)[:, :k]
         ops.scale_cols_f64(vt, torch.rsqrt(theta_t).to(dev), out=vs)
         ops.dgemm(chol.T, vs, out=z[:, :k])
-    ops.qr_rotate(chol, z)                                           # chol <- L Q_H: columns j < k are +-V_t sqrt(theta_j)
+    split.rotate(chol, z)                                            # chol <- L Q_H: columns j < k are +-V_t sqrt(theta_j)
     scale = torch.full((n,), 1.0 / tau, dtype=f64)
     scale[:k] = 1.0 / theta_t
     st = ops.transpose_scale_f64(ops.scale_cols_f64(chol, scale.to(dev)), 1.0)

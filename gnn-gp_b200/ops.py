@@ -532,8 +532,9 @@ class CudaOps(object):
         n = kmm.shape[0]
         if kmm.shape[1] != n:
             raise RuntimeError("sym_f64: square block expected")
-        out = torch.empty((n, n), dtype=torch.float64, device=kmm.device)
-        self.lib.call("gnngp_sym_f64_from_f32", kmm.data_ptr(), ldk, n, out.data_ptr(), n, self._stream())
+        ld = n + (n & 1)                                             # even pitch: the fp64 GEMM's aligned fast path
+        out = torch.empty((n, ld), dtype=torch.float64, device=kmm.device)[:, :n]
+        self.lib.call("gnngp_sym_f64_from_f32", kmm.data_ptr(), ldk, n, out.data_ptr(), ld, self._stream())
         return out
 
     def dgemm(self, A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, alpha: float = 1.0, beta: float = 0.0,
@@ -567,8 +568,9 @@ class CudaOps(object):
         """One block of at most 128 rows: Cholesky factor in place (lower triangle) and the returned ``L⁻¹``."""
         self._f64_view(G, "G")
         nb = G.shape[0]
-        linv = torch.empty((nb, nb), dtype=torch.float64, device=G.device)
-        self.lib.call("gnngp_potrf_inv_block_f64", G.data_ptr(), G.stride(0), nb, linv.data_ptr(), nb, info.data_ptr(),
+        ldi = nb + (nb & 1)                                          # even pitch (aligned GEMM fast path)
+        linv = torch.empty((nb, ldi), dtype=torch.float64, device=G.device)[:, :nb]
+        self.lib.call("gnngp_potrf_inv_block_f64", G.data_ptr(), G.stride(0), nb, linv.data_ptr(), ldi, info.data_ptr(),
                       self._stream())
         return linv
 
@@ -587,16 +589,16 @@ class CudaOps(object):
                       self._stream())
         return X
 
-    def krylov_root(self, kmm: torch.Tensor, stats: Optional[dict] = None):
+    def krylov_root(self, kmm: torch.Tensor, stats: Optional[dict] = None, comm=None):
         """The Nystrom root of a landmark block by ``krylov_root.root_factors`` (an operator so that it shows up as ONE
         stage in the bench's timing table); ``None`` when the route hands the block back."""
         from . import krylov_root as route
-        return route.root_factors(self, kmm, stats)
+        return route.root_factors(self, kmm, stats, comm=comm)
 
-    def krylov_fit(self, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Tensor, stats: Optional[dict] = None):
+    def krylov_fit(self, gram: torch.Tensor, qty_t: torch.Tensor, shifts: torch.Tensor, stats: Optional[dict] = None, comm=None):
         """All nuggets' coefficient blocks by ``krylov_fit.coefficients`` (one timed stage); ``None`` = not converged."""
         from . import krylov_fit as route
-        return route.coefficients(self, gram, qty_t, shifts, stats)
+        return route.coefficients(self, gram, qty_t, shifts, stats, comm=comm)
 
     def band_solve(self, H: torch.Tensor, rhs_t: torch.Tensor, shifts: torch.Tensor):
         """``(band(H) + shifts[g] I) x = rhs`` for every shift (the band |i - j| <= 128 of the lower triangle of the fp64

@@ -105,7 +105,8 @@ class Pipeline(object):
         if krylov_root.wanted(kmm.shape[0], ops):
             stats = {}
             route = getattr(ops, "krylov_root", None)                 # (the CUDA operator set wraps it as one timed stage)
-            got = route(kmm, stats) if route is not None else krylov_root.root_factors(ops, kmm, stats)
+            got = (route(kmm, stats, comm=self.comm) if route is not None
+                   else krylov_root.root_factors(ops, kmm, stats, comm=self.comm))
             self.last_root_stats = ops.last_root_stats = stats
             got = got if self._all_ranks(got is not None, kmm.device) else None
             if got is not None:
@@ -553,7 +554,8 @@ class Pipeline(object):
         shifts = (nugget.to(torch.float64) * scale.to(torch.float64)).contiguous()
         stats = {}
         route = getattr(ops, "krylov_fit", None)
-        coeff_t = route(gram, qty_t, shifts, stats) if route is not None else krylov_fit.coefficients(ops, gram, qty_t, shifts, stats)
+        coeff_t = (route(gram, qty_t, shifts, stats, comm=self.comm) if route is not None
+                   else krylov_fit.coefficients(ops, gram, qty_t, shifts, stats, comm=self.comm))
         self.last_fit_stats = ops.last_fit_stats = stats
         if not self._all_ranks(coeff_t is not None, gram.device):
             return None

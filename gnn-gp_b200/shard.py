@@ -125,6 +125,13 @@ class TorchComm(object):
         self.bytes_reduced += t.numel() * t.element_size()
         return t
 
+    def all_gather_equal(self, piece: Tensor, out: Tensor) -> Tensor:
+        """Equal-sized contiguous pieces (rank order) → ``out`` [world * piece.shape[0], ...] on every rank (any dtype):
+        the row blocks of the replicated Krylov routes' products."""
+        dist.all_gather_into_tensor(out, piece, group=self.group)
+        self.bytes_gathered += out.numel() * out.element_size()
+        return out
+
     def all_gather_rows(self, block: Tensor, layout: RowLayout) -> Tensor:
         """[n_local x k] row blocks (rank order = row order) → the full [N x k] matrix on every rank."""
         n_local, k = block.shape

@@ -95,3 +95,46 @@ def test_row_layout_partitions_every_row_once():
                 pos_all.append(pos)
                 assert bool(mask[rows + RowLayout(n, world, r).begin].all())
             assert torch.equal(torch.cat(pos_all), torch.arange(int(mask.sum())))
+
+
+def _rowsplit_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    from stub_ops import StubOps
+    from gnngp_b200.krylov_root import RowSplit
+    from gnngp_b200.shard import TorchComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gen = torch.Generator().manual_seed(4)
+    n, c, k = 301, 7, 256
+    m = torch.randn(n, n, generator=gen, dtype=torch.float64)
+    v = torch.randn(n, c, generator=gen, dtype=torch.float64)
+    zq, _ = torch.linalg.qr(torch.randn(n, 40, generator=gen, dtype=torch.float64))
+    z = torch.zeros(n, k, dtype=torch.float64)
+    z[:, :40] = zq
+    ops = StubOps()
+    split = RowSplit(ops, n, TorchComm())
+    out = torch.empty(n, c, dtype=torch.float64)
+    split.matmul(m, v, out)
+    x = m.clone()
+    split.rotate(x, z.clone())
+    want_x = m.clone()
+    ops.qr_rotate(want_x, z.clone())
+    ok = bool(torch.allclose(out, m @ v, rtol=1e-12, atol=1e-12)) and bool(torch.allclose(x, want_x, rtol=1e-10, atol=1e-10))
+    torch.save({"ok": ok, "rows": (split.r0, split.r1)}, os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_split_products_and_rotation(tmp_path, world):
+    """krylov_root.RowSplit: the rank-parallel product / rotation of the replicated Krylov routes equals the local one
+    on every rank (odd row count, last rank short)."""
+    mp.spawn(_rowsplit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    spans = []
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), "rank%d.pt" % r))
+        assert got["ok"], r
+        spans.append(got["rows"])
+    assert spans[0][0] == 0 and spans[-1][1] == 301 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
