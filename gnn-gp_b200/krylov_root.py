@@ -29,8 +29,9 @@ On the benchmark graph 647 of 15 404 eigenvalues lie above the clamp: instead of
     dimension ~0.11 n; every product ``M V_j`` is one fp64 GEMM) and a Rayleigh–Ritz step on the small projected matrix,
   * one skinny GEMM for ``Z``, a Householder QR of the n x k block ``Z`` and its block reflectors applied to ``L``.
 
-Everything is fp64: ``S`` cancels ``L / tau`` against the top of the spectrum (1/tau against 1/lam_max = 1e-4 / tau), which
-needs the top Ritz vectors to ~1e-10; a Ritz pair (theta, y) is accepted when ``|M y - theta y| <= tol * tau * theta_max /
+Everything is fp64: the bulk columns carry the scale 1/tau against 1/lam_max = 1e-4/tau for the top direction, so they must
+be orthogonal to the top Ritz directions to ~1e-10 (a leak of 1e-6 would already double the top entry of ``S Sᵀ``), which
+needs the top Ritz vectors that accurate; a Ritz pair (theta, y) is accepted when ``|M y - theta y| <= tol * tau * theta_max /
 theta`` (the residual bound under which the error of ``Q Qᵀ`` stays below ~1e-8, measured against the full
 eigendecomposition on the benchmark's landmark block: 1.7e-10 at Krylov dimension 1 664).  When the Cholesky factorisation
 meets a non-positive pivot (an indefinite or rank-deficient block, which the reference's clamp tolerates) or the Ritz
