@@ -87,4 +87,7 @@ def library() -> Library:
         engine = os.environ.get("GNNGP_GEMM_ENGINE")
         if engine is not None:
             _LIBRARY.cdll.gnngp_set_gemm_engine(int(engine))
+        flags = os.environ.get("GNNGP_SPMM_FLAGS")
+        if flags is not None:
+            _LIBRARY.cdll.gnngp_spmm_set_flags(int(flags))
     return _LIBRARY

@@ -20,11 +20,77 @@
 //    the byte offset of the B row and stages {offset, value} in shared memory, from where every lane
 //    fetches it with one broadcast LDS.128; four gathers are in flight per lane before the FMAs.
 //  * columns beyond the last full tile go through the scalar, bounds-checked instantiation.
+//  * tuning flags (gnngp_spmm_set_flags; default 0 = none): 1 = rows owned by one work item leave with one
+//    16-byte streaming store per lane (st.global.cs: the C lines of a tile pass, as many bytes as the panel
+//    being gathered, stop competing with that panel for the L2), 2 = the gathers carry an L2 evict_last
+//    policy (short rows reuse a B strip only ~avg-degree times per tile pass, too rarely for plain LRU to keep
+//    it against the C and adjacency streams), 4 = only the rows that need it (cut by a work-item border, or
+//    empty) are zero-filled instead of the whole C.
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
 namespace gnngp {
+
+enum : int { SPMM_STREAM_C = 1, SPMM_KEEP_B = 2, SPMM_ZERO_CUT_ROWS = 4, SPMM_ALL_FLAGS = 7 };
+static std::atomic<int> g_spmm_flags{0};
+
+__device__ __forceinline__ uint64_t l2_evict_last_policy()
+{
+    uint64_t policy;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+// 16-byte read-only gather; KEEP: with the L2 evict_last policy
+template <bool KEEP>
+__device__ __forceinline__ float4 gather16(const void *p, uint64_t policy)
+{
+    if constexpr (KEEP) {
+        float4 v;
+        asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+            : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+            : "l"(p), "l"(policy));
+        return v;
+    } else {
+        return __ldg(reinterpret_cast<const float4 *>(p));
+    }
+}
+
+// Rows that are not written by exactly one work item: cut by a border of the nnz-balanced split (their pieces
+// are combined with atomics) or empty (never visited).  One warp per row.
+__global__ void zero_cut_rows_kernel(const int64_t *__restrict__ rowptr, int64_t n_rows, int64_t chunk,
+                                     float *__restrict__ C, int64_t ldc, int64_t k, bool vec_ok)
+{
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t rs = __ldg(rowptr + row), re = __ldg(rowptr + row + 1);
+    if (re > rs && rs / chunk == (re - 1) / chunk) return;         // wholly inside one work item: stored, not added
+    const int lane = threadIdx.x & 31;
+    float *out = C + row * ldc;
+    int64_t c = 0;
+    if (vec_ok) {
+        for (c = (int64_t)lane * 4; c + 3 < k; c += 128) *reinterpret_cast<float4 *>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        c = (k / 4) * 4 + lane;
+    } else {
+        c = lane;
+    }
+    for (; c < k; c += 32) out[c] = 0.0f;
+}
+
+static int zero_fill(const int64_t *rowptr, int64_t n_rows, int64_t chunk, float *C, int64_t ldc, int64_t k, int flags,
+                     cudaStream_t st)
+{
+    if (flags & SPMM_ZERO_CUT_ROWS) {
+        zero_cut_rows_kernel<<<(unsigned)ceil_div(n_rows, 8), 256, 0, st>>>(rowptr, n_rows, chunk, C, ldc, k,
+                                                                            aligned(C, 16) && ldc % 4 == 0);
+        GNNGP_LAUNCHED();
+    } else {
+        GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
+    }
+    return GNNGP_OK;
+}
 
 template <int VEC>
 struct Vec;
@@ -52,13 +118,16 @@ __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&ou
 constexpr int kWarpsPerBlock = 8;
 constexpr int kUnroll = 4;
 
-template <int VEC, int SPLIT, bool CHECK>
+template <int VEC, int SPLIT, bool CHECK, bool KEEP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                 const float *__restrict__ vals, int64_t n_rows, int64_t nnz, const float *__restrict__ B,
                 int64_t ldb, int64_t col_begin, int64_t col_end, float alpha, float *__restrict__ C, int64_t ldc,
-                int64_t chunk, int64_t n_chunks, int64_t n_tiles)
+                int64_t chunk, int64_t n_chunks, int64_t n_tiles, bool stream_c)
 {
+    static_assert(!KEEP || VEC == 4, "the evict_last gathers are 16-byte loads");
+    uint64_t policy = 0;
+    if constexpr (KEEP) policy = l2_evict_last_policy();
     constexpr int LANES = 32 / SPLIT;
     constexpr int TW = LANES * VEC;
     constexpr int GROUP = kUnroll * SPLIT;             // nonzeros consumed per unrolled step
@@ -123,7 +192,12 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         const int64_t off = ((int64_t)ent[u].y << 32) | (uint32_t)ent[u].x;
-                        load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b[u]);
+                        if constexpr (KEEP) {
+                            const float4 t = gather16<true>(bcol + off, policy);
+                            b[u][0] = t.x; b[u][1] = t.y; b[u][2] = t.z; b[u][3] = t.w;
+                        } else {
+                            load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b[u]);
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u)
@@ -136,7 +210,12 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
                 if (col_ok) {
                     float b[VEC];
                     const int64_t off = ((int64_t)ent.y << 32) | (uint32_t)ent.x;
-                    load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b);
+                    if constexpr (KEEP) {
+                        const float4 t = gather16<true>(bcol + off, policy);
+                        b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+                    } else {
+                        load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b);
+                    }
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) acc[e] = fmaf(__int_as_float(ent.z), b[e], acc[e]);
                 }
@@ -150,8 +229,18 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
             float *out = C + row * ldc + (mycol - col_begin);
             const bool whole = (rstart >= p0) && (rend <= p1);
             if (whole) {
+                bool stored = false;
+                if constexpr (VEC == 4) {
+                    if (stream_c) {             // the host sets it only with 16-byte aligned C rows
+                        __stcs(reinterpret_cast<float4 *>(out),
+                               make_float4(alpha * acc[0], alpha * acc[1], alpha * acc[2], alpha * acc[3]));
+                        stored = true;
+                    }
+                }
+                if (!stored) {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) out[e] = alpha * acc[e];
+                    for (int e = 0; e < VEC; ++e) out[e] = alpha * acc[e];
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) atomicAdd(out + e, alpha * acc[e]);
@@ -162,10 +251,10 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
     }
 }
 
-template <int VEC, int SPLIT, bool CHECK>
+template <int VEC, int SPLIT, bool CHECK, bool KEEP = false>
 static int launch(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows, int64_t nnz,
                   const float *B, int64_t ldb, int64_t col_begin, int64_t col_end, float alpha, float *C,
-                  int64_t ldc, int64_t chunk, cudaStream_t st)
+                  int64_t ldc, int64_t chunk, cudaStream_t st, bool stream_c = false)
 {
     constexpr int TW = 32 / SPLIT * VEC;
     const int64_t n_tiles = ceil_div(col_end - col_begin, TW);
@@ -173,8 +262,9 @@ static int launch(const int64_t *rowptr, const int32_t *colidx, const float *val
     const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
     if (blocks <= 0) return GNNGP_OK;
     GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
-    spmm_csr_kernel<VEC, SPLIT, CHECK><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-        rowptr, colidx, vals, n_rows, nnz, B, ldb, col_begin, col_end, alpha, C + col_begin, ldc, chunk, n_chunks, n_tiles);
+    spmm_csr_kernel<VEC, SPLIT, CHECK, KEEP><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+        rowptr, colidx, vals, n_rows, nnz, B, ldb, col_begin, col_end, alpha, C + col_begin, ldc, chunk, n_chunks, n_tiles,
+        stream_c && aligned(C + col_begin, 16) && ldc % 4 == 0);
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }
@@ -246,11 +336,14 @@ __global__ void panelize_peers_kernel(const float *const *__restrict__ peer, int
 
 constexpr int kPanelUnroll = 8;      // gathers in flight per lane (two half-warps -> 16 nonzeros per step)
 
+template <bool KEEP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const float *__restrict__ vals,
                   int64_t n_rows, int64_t nnz, const float *__restrict__ P, int64_t n_cols, int64_t k, float alpha,
-                  float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks, int64_t n_tiles)
+                  float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks, int64_t n_tiles, bool stream_c)
 {
+    uint64_t policy = 0;
+    if constexpr (KEEP) policy = l2_evict_last_policy();
     constexpr int GROUP = kPanelUnroll * 2;
     __shared__ int2 staged[kWarpsPerBlock][32];          // {column id, value bits} of the current batch
     int2 *stage = staged[threadIdx.x >> 5];
@@ -297,7 +390,7 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
     uint64_t base64 = reinterpret_cast<uint64_t>(base);
     asm volatile("" : "+l"(base64));
     auto gather = [&](int col) {
-        return __ldg(reinterpret_cast<const float4 *>(base64 + (uint64_t)(uint32_t)col * 256u));   // n_cols < 2^24
+        return gather16<KEEP>(reinterpret_cast<const void *>(base64 + (uint64_t)(uint32_t)col * 256u), policy);   // n_cols < 2^24
     };
     int batch = 0;                                        // first nonzero (relative) of the staged batch
     int2 ahead = fetch(32);
@@ -362,10 +455,14 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
             float *out = C + row * ldc + mycol;
             const float r[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
             const bool whole = (rstart >= p0) && (rend <= p1);
+            if (whole && stream_c && mycol + 3 < k) {     // the host sets stream_c only with 16-byte aligned C rows
+                __stcs(reinterpret_cast<float4 *>(out), make_float4(r[0], r[1], r[2], r[3]));
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (mycol + e < k) {
-                    if (whole) out[e] = r[e]; else atomicAdd(out + e, r[e]);
+                for (int e = 0; e < 4; ++e) {
+                    if (mycol + e < k) {
+                        if (whole) out[e] = r[e]; else atomicAdd(out + e, r[e]);
+                    }
                 }
             }
         }
@@ -374,6 +471,32 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
 }
 
 }  // namespace gnngp
+
+namespace gnngp {
+static int launch_panels(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows, int64_t nnz,
+                         const float *panels, int64_t n_cols, int64_t k, float alpha, float *C, int64_t ldc, int64_t chunk,
+                         int flags, cudaStream_t st)
+{
+    const int64_t n_tiles = ceil_div(k, PANEL);
+    const int64_t n_chunks = ceil_div(nnz, chunk);
+    const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
+    GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
+    const bool stream_c = (flags & SPMM_STREAM_C) && aligned(C, 16) && ldc % 4 == 0;
+    if (flags & SPMM_KEEP_B)
+        spmm_panel_kernel<true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k,
+                                                                              alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c);
+    else
+        spmm_panel_kernel<false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k,
+                                                                               alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c);
+    GNNGP_LAUNCHED();
+    return GNNGP_OK;
+}
+}  // namespace gnngp
+
+extern "C" int gnngp_spmm_set_flags(int flags)
+{
+    return gnngp::g_spmm_flags.exchange(flags & gnngp::SPMM_ALL_FLAGS);
+}
 
 extern "C" size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k)
 {
@@ -418,18 +541,17 @@ extern "C" int gnngp_spmm_panels_f32(const int64_t *rowptr, const int32_t *colid
     GNNGP_REQUIRE(rowptr && C && panels && (nnz == 0 || (colidx && vals)), "spmm_panels: null pointer");
     GNNGP_REQUIRE(n_cols < ((int64_t)1 << 24), "spmm_panels: too many columns for the panel addressing");
     cudaStream_t st = as_stream(stream);
-    GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
-    if (nnz == 0) return GNNGP_OK;
+    const int flags = g_spmm_flags.load();
+    if (nnz == 0) {
+        GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
+        return GNNGP_OK;
+    }
     int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : (nnz >= ((int64_t)1 << 25) ? 1024 : 512);
     const int64_t n_tiles = ceil_div(k, PANEL);
     while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * n_tiles < (int64_t)sm_count() * 32) chunk >>= 1;
-    const int64_t n_chunks = ceil_div(nnz, chunk);
-    const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
-    GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm_panels: grid of %lld blocks is too large", (long long)blocks);
-    spmm_panel_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k, alpha, C,
-                                                                    ldc, chunk, n_chunks, n_tiles);
-    GNNGP_LAUNCHED();
-    return GNNGP_OK;
+    int rc = zero_fill(rowptr, n_rows, chunk, C, ldc, k, flags, st);
+    if (rc != GNNGP_OK) return rc;
+    return launch_panels(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k, alpha, C, ldc, chunk, flags, st);
 }
 
 extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows,
@@ -446,8 +568,11 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
                   "spmm: tile_cols must be 0, 32, 64 or 128");
     if (k == 0) return GNNGP_OK;
     cudaStream_t st = as_stream(stream);
-    GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
-    if (nnz == 0) return GNNGP_OK;
+    const int flags = g_spmm_flags.load();
+    if (nnz == 0) {
+        GNNGP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)k * sizeof(float), (size_t)n_rows, st));
+        return GNNGP_OK;
+    }
 
     // work-item size: 1024 nonzeros on large graphs (Reddit shape: 108 ms vs 112 ms at 512), 512 otherwise
     int64_t chunk = nnz_per_warp > 0 ? nnz_per_warp : (nnz >= ((int64_t)1 << 25) ? 1024 : 512);
@@ -467,13 +592,9 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
             B, ldb, n_cols, k, n_tiles, panels, aligned(B, 16) && ldb % 4 == 0);
         GNNGP_LAUNCHED();
         while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * n_tiles < (int64_t)sm_count() * 32) chunk >>= 1;
-        const int64_t n_chunks = ceil_div(nnz, chunk);
-        const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
-        GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
-        spmm_panel_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k,
-                                                                        alpha, C, ldc, chunk, n_chunks, n_tiles);
-        GNNGP_LAUNCHED();
-        return GNNGP_OK;
+        const int rcz = zero_fill(rowptr, n_rows, chunk, C, ldc, k, flags, st);
+        if (rcz != GNNGP_OK) return rcz;
+        return launch_panels(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k, alpha, C, ldc, chunk, flags, st);
     }
 
     // ---- row-major path (no workspace, or an explicit tile width): gathers straight from B
@@ -491,10 +612,14 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
     while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * ceil_div(k, tw) < (int64_t)sm_count() * 32) chunk >>= 1;
 
     const int64_t k_full = (k / tw) * tw;
-    int rc = GNNGP_OK;
+    int rc = zero_fill(rowptr, n_rows, chunk, C, ldc, k, flags, st);
+    if (rc != GNNGP_OK) return rc;
+    const bool stream_c = (flags & SPMM_STREAM_C) != 0, keep = (flags & SPMM_KEEP_B) != 0;
     if (k_full > 0) {
-        if (vec == 4 && tw == 128) rc = launch<4, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);
-        else if (vec == 4 && tw == 64) rc = launch<4, 2, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);
+        if (vec == 4 && tw == 128 && keep) rc = launch<4, 1, false, true>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
+        else if (vec == 4 && tw == 64 && keep) rc = launch<4, 2, false, true>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
+        else if (vec == 4 && tw == 128) rc = launch<4, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
+        else if (vec == 4 && tw == 64) rc = launch<4, 2, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
         else if (vec == 4 && tw == 32) rc = launch<2, 2, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);
         else if (vec == 2 && tw == 64) rc = launch<2, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);
         else if (vec == 2 && tw == 32) rc = launch<2, 2, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);

@@ -64,6 +64,8 @@ class CudaOps(object):
         self._csr_cache = {}
         self.spmm_tile_cols = 0       # 0 = panel layout (default); 32/64/128 = row-major gather with that tile
         self.spmm_nnz_per_warp = 0
+        # GNNGP_SPMM_PANELS = 1 / 0 forces / forbids the 64-column panel copy of the gathered operand (default: by shape)
+        self.spmm_panels_mode = os.environ.get("GNNGP_SPMM_PANELS", "auto")
         self.spmm_kernel_by_k = {}    # operand width -> name of the kernel the last product of that width ran (bench roofline)
 
     # ------------------------------------------------------------------ plumbing
@@ -144,6 +146,10 @@ class CudaOps(object):
 
     def set_gemm_engine(self, engine: int) -> int:
         return int(self.lib.query("gnngp_set_gemm_engine", int(engine)))
+
+    def set_spmm_flags(self, flags: int) -> int:
+        """Cache-behaviour flags of the SpMM kernels (``gnngp_spmm_set_flags``); returns the previous setting."""
+        return int(self.lib.query("gnngp_spmm_set_flags", int(flags)))
 
     # ------------------------------------------------------------------ adjacency
     def csr_from_coo(self, row: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n_rows: int, n_cols: int,
@@ -309,6 +315,8 @@ class CudaOps(object):
         # and wide / misaligned operands (Reddit shape: 108 vs 121 ms at k=3024, 22 vs 26 ms at k=602); for
         # short rows (arxiv shape, 15 nonzeros per row) gathering straight from the row-major operand wins.
         use_panels = int(self.spmm_tile_cols) == 0 and csr.nnz >= 64 * csr.n_rows and k >= 256
+        if self.spmm_panels_mode in ("0", "1") and int(self.spmm_tile_cols) == 0:
+            use_panels = self.spmm_panels_mode == "1" and csr.n_cols < (1 << 24)
         if use_panels:
             need = self.lib.query("gnngp_spmm_workspace_bytes", csr.n_cols, k)
             ws = self.workspace(need + 256, B.device, "spmm")

@@ -68,6 +68,13 @@ int gnngp_csr_from_coo(const int64_t *row, const int64_t *col, const float *val,
  * nnz_per_warp: nonzeros per warp work item (0 = default: 512, or 1024 on graphs with >= 2^25 nonzeros).  Rows that straddle a work item are
  * combined with fp32 atomics, so C is zero-filled first (the call does that itself). */
 size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k);
+/* Cache-behaviour flags of the SpMM kernels (results do not depend on them); returns the previous setting.
+ * 1: rows written by a single work item leave with one 16-byte streaming store per lane (when C's rows are
+ *    16-byte aligned), so a tile pass's C lines do not compete with the B tile for the L2;
+ * 2: the B gathers carry an L2 evict_last policy;
+ * 4: only rows that are accumulated with atomics (cut by a work-item border) or empty are zero-filled,
+ *    instead of the whole C. */
+int gnngp_spmm_set_flags(int flags);
 int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals,
                        int64_t n_rows, int64_t n_cols, int64_t nnz, const float *B, int64_t ldb,
                        int64_t k, float alpha, float *C, int64_t ldc, int tile_cols, int nnz_per_warp,
