@@ -20,12 +20,14 @@
 //    the byte offset of the B row and stages {offset, value} in shared memory, from where every lane
 //    fetches it with one broadcast LDS.128; four gathers are in flight per lane before the FMAs.
 //  * columns beyond the last full tile go through the scalar, bounds-checked instantiation.
-//  * tuning flags (gnngp_spmm_set_flags; default 0 = none): 1 = rows owned by one work item leave with one
-//    16-byte streaming store per lane (st.global.cs: the C lines of a tile pass, as many bytes as the panel
-//    being gathered, stop competing with that panel for the L2), 2 = the gathers carry an L2 evict_last
-//    policy (short rows reuse a B strip only ~avg-degree times per tile pass, too rarely for plain LRU to keep
-//    it against the C and adjacency streams), 4 = only the rows that need it (cut by a work-item border, or
-//    empty) are zero-filled instead of the whole C.
+//  * tuning flags (gnngp_spmm_set_flags): 1 = rows owned by one work item leave with one 16-byte streaming store
+//    per lane (st.global.cs), 2 = only the rows that need it (cut by a work-item border, or empty) are zero-filled
+//    instead of the whole C, 4 = graphs with short rows (< 64 nonzeros per row on average) take
+//    spmm_short_rows_kernel: the gathers of a work item are issued four nonzeros at a time WHATEVER rows they
+//    belong to (row ends are looked up in a register cache of the next 32 row pointers), so a 15-nonzero row no
+//    longer costs a serial rowptr -> colidx -> gather -> reduce -> store chain of its own.
+//    (An L2 evict_last policy on the gathers was measured too, profiles/r2/call28_spmm_policy.json: no effect at
+//    either shape, so it is not kept.)
 #include <algorithm>
 #include <atomic>
 
@@ -33,30 +35,8 @@
 
 namespace gnngp {
 
-enum : int { SPMM_STREAM_C = 1, SPMM_KEEP_B = 2, SPMM_ZERO_CUT_ROWS = 4, SPMM_ALL_FLAGS = 7 };
-static std::atomic<int> g_spmm_flags{0};
-
-__device__ __forceinline__ uint64_t l2_evict_last_policy()
-{
-    uint64_t policy;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    return policy;
-}
-
-// 16-byte read-only gather; KEEP: with the L2 evict_last policy
-template <bool KEEP>
-__device__ __forceinline__ float4 gather16(const void *p, uint64_t policy)
-{
-    if constexpr (KEEP) {
-        float4 v;
-        asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-            : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-            : "l"(p), "l"(policy));
-        return v;
-    } else {
-        return __ldg(reinterpret_cast<const float4 *>(p));
-    }
-}
+enum : int { SPMM_STREAM_C = 1, SPMM_ZERO_CUT_ROWS = 2, SPMM_SHORT_ROWS = 4, SPMM_ALL_FLAGS = 7 };
+static std::atomic<int> g_spmm_flags{SPMM_STREAM_C | SPMM_ZERO_CUT_ROWS};
 
 // Rows that are not written by exactly one work item: cut by a border of the nnz-balanced split (their pieces
 // are combined with atomics) or empty (never visited).  One warp per row.
@@ -118,16 +98,13 @@ __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&ou
 constexpr int kWarpsPerBlock = 8;
 constexpr int kUnroll = 4;
 
-template <int VEC, int SPLIT, bool CHECK, bool KEEP>
+template <int VEC, int SPLIT, bool CHECK>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                 const float *__restrict__ vals, int64_t n_rows, int64_t nnz, const float *__restrict__ B,
                 int64_t ldb, int64_t col_begin, int64_t col_end, float alpha, float *__restrict__ C, int64_t ldc,
                 int64_t chunk, int64_t n_chunks, int64_t n_tiles, bool stream_c)
 {
-    static_assert(!KEEP || VEC == 4, "the evict_last gathers are 16-byte loads");
-    uint64_t policy = 0;
-    if constexpr (KEEP) policy = l2_evict_last_policy();
     constexpr int LANES = 32 / SPLIT;
     constexpr int TW = LANES * VEC;
     constexpr int GROUP = kUnroll * SPLIT;             // nonzeros consumed per unrolled step
@@ -192,12 +169,7 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         const int64_t off = ((int64_t)ent[u].y << 32) | (uint32_t)ent[u].x;
-                        if constexpr (KEEP) {
-                            const float4 t = gather16<true>(bcol + off, policy);
-                            b[u][0] = t.x; b[u][1] = t.y; b[u][2] = t.z; b[u][3] = t.w;
-                        } else {
-                            load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b[u]);
-                        }
+                        load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u)
@@ -210,12 +182,7 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
                 if (col_ok) {
                     float b[VEC];
                     const int64_t off = ((int64_t)ent.y << 32) | (uint32_t)ent.x;
-                    if constexpr (KEEP) {
-                        const float4 t = gather16<true>(bcol + off, policy);
-                        b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-                    } else {
-                        load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b);
-                    }
+                    load_row<VEC>(reinterpret_cast<const float *>(bcol + off), b);
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) acc[e] = fmaf(__int_as_float(ent.z), b[e], acc[e]);
                 }
@@ -251,7 +218,126 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
     }
 }
 
-template <int VEC, int SPLIT, bool CHECK, bool KEEP = false>
+// ---------------------------------------------------------------------------------------------
+// Short rows (arxiv shape: 15 nonzeros per row).  In spmm_csr_kernel every row is a serial chain
+// rowptr -> (colidx, vals) -> gathers -> store and a warp has one row in flight; with rows this short the
+// launch is bound by that latency, not by HBM or the L2 (measured: 14.7 ms against 1.9 ms of HBM time).
+// Here the (colidx, vals) stream of the work item is consumed in fixed groups of kShortUnroll nonzeros,
+// independent of the row structure: the gathers of a group are issued together, the products are added into
+// the running row accumulator in nonzero order, and a row is flushed when the position reaches its end.  Row
+// ends come from a per-warp register cache of the next 32 row pointers (one coalesced load per 32 rows, read
+// with a shuffle).  One warp = one nonzero per gather instruction, 128 columns (16 bytes per lane).
+constexpr int kShortUnroll = 4;
+constexpr int kShortTile = 128;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_short_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                       const float *__restrict__ vals, int64_t n_rows, int64_t nnz, const float *__restrict__ B,
+                       int64_t ldb, float alpha, float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks,
+                       int64_t n_tiles, bool stream_c, bool vec_c)
+{
+    __shared__ int4 staged[kWarpsPerBlock][32];
+    int4 *stage = staged[threadIdx.x >> 5];
+
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (item >= n_chunks * n_tiles) return;
+    const int64_t tile = item / n_chunks;
+    const int64_t piece = item - tile * n_chunks;
+    const int64_t mycol = tile * kShortTile + (int64_t)lane * 4;
+    const char *bcol = reinterpret_cast<const char *>(B + mycol);
+    const int64_t row_bytes = ldb * (int64_t)sizeof(float);
+
+    const int64_t p0 = piece * chunk;
+    const int len = (int)(min(p0 + chunk, nnz) - p0);
+
+    int64_t lo = 0, hi = n_rows - 1;                      // largest row with rowptr[row] <= p0 (it holds nonzero p0)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(rowptr + mid) <= p0) lo = mid; else hi = mid - 1;
+    }
+    int64_t row = lo;
+    bool starts_here = __ldg(rowptr + row) >= p0;         // false: the first row began in an earlier work item
+    // row ends relative to p0, 32 at a time: lane i holds the end of row (cache_base + i)
+    auto load_ends = [&](int64_t base) {
+        const int64_t r = min(base + 1 + lane, n_rows);
+        return (int)min(__ldg(rowptr + r) - p0, (int64_t)1 << 30);
+    };
+    int ends = load_ends(row);
+    int cached = 0;                                       // index of `row` inside the cache
+    int rend = __shfl_sync(0xffffffffu, ends, 0);
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool has = false;                                     // the current row has received a nonzero of this item
+    auto flush = [&](bool whole) {
+        float *out = C + row * ldc + mycol;
+        const float r[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
+        if (whole) {
+            if (vec_c) {
+                const float4 v = make_float4(r[0], r[1], r[2], r[3]);
+                if (stream_c) __stcs(reinterpret_cast<float4 *>(out), v); else *reinterpret_cast<float4 *>(out) = v;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) out[e] = r[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(out + e, r[e]);
+        }
+    };
+
+    for (int q = 0; q < len; q += 32) {
+        const int mine = q + lane;
+        int4 entry = make_int4(0, 0, 0, 0);
+        if (mine < len) {
+            const int64_t off = (int64_t)__ldcs(colidx + p0 + mine) * row_bytes;
+            entry.x = (int)(uint32_t)off;
+            entry.y = (int)(off >> 32);
+            entry.z = __float_as_int(__ldcs(vals + p0 + mine));
+        }
+        __syncwarp();
+        stage[lane] = entry;
+        __syncwarp();
+        const int cnt = min(32, len - q);
+        for (int j = 0; j < cnt; j += kShortUnroll) {
+            int4 ent[kShortUnroll];
+            float4 b[kShortUnroll];
+#pragma unroll
+            for (int u = 0; u < kShortUnroll; ++u) ent[u] = stage[min(j + u, 31)];
+#pragma unroll
+            for (int u = 0; u < kShortUnroll; ++u) {
+                if (j + u < cnt) {
+                    const int64_t off = ((int64_t)ent[u].y << 32) | (uint32_t)ent[u].x;
+                    b[u] = __ldg(reinterpret_cast<const float4 *>(bcol + off));
+                } else {
+                    b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kShortUnroll; ++u) {
+                const int pos = q + j + u;
+                if (j + u < cnt) {
+                    while (pos == rend) {                 // the current row ended before this nonzero (loop: empty rows)
+                        if (has) flush(starts_here);
+                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        has = false;
+                        starts_here = true;
+                        ++row;
+                        if (++cached == 32) { ends = load_ends(row); cached = 0; }
+                        rend = __shfl_sync(0xffffffffu, ends, cached);
+                    }
+                    const float v = __int_as_float(ent[u].z);
+                    acc.x = fmaf(v, b[u].x, acc.x); acc.y = fmaf(v, b[u].y, acc.y);
+                    acc.z = fmaf(v, b[u].z, acc.z); acc.w = fmaf(v, b[u].w, acc.w);
+                    has = true;
+                }
+            }
+        }
+    }
+    if (has) flush(starts_here && rend <= len);           // the last row: whole only if it also ends inside the item
+}
+
+template <int VEC, int SPLIT, bool CHECK>
 static int launch(const int64_t *rowptr, const int32_t *colidx, const float *vals, int64_t n_rows, int64_t nnz,
                   const float *B, int64_t ldb, int64_t col_begin, int64_t col_end, float alpha, float *C,
                   int64_t ldc, int64_t chunk, cudaStream_t st, bool stream_c = false)
@@ -262,7 +348,7 @@ static int launch(const int64_t *rowptr, const int32_t *colidx, const float *val
     const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
     if (blocks <= 0) return GNNGP_OK;
     GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
-    spmm_csr_kernel<VEC, SPLIT, CHECK, KEEP><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+    spmm_csr_kernel<VEC, SPLIT, CHECK><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
         rowptr, colidx, vals, n_rows, nnz, B, ldb, col_begin, col_end, alpha, C + col_begin, ldc, chunk, n_chunks, n_tiles,
         stream_c && aligned(C + col_begin, 16) && ldc % 4 == 0);
     GNNGP_LAUNCHED();
@@ -336,14 +422,11 @@ __global__ void panelize_peers_kernel(const float *const *__restrict__ peer, int
 
 constexpr int kPanelUnroll = 8;      // gathers in flight per lane (two half-warps -> 16 nonzeros per step)
 
-template <bool KEEP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const float *__restrict__ vals,
                   int64_t n_rows, int64_t nnz, const float *__restrict__ P, int64_t n_cols, int64_t k, float alpha,
                   float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks, int64_t n_tiles, bool stream_c)
 {
-    uint64_t policy = 0;
-    if constexpr (KEEP) policy = l2_evict_last_policy();
     constexpr int GROUP = kPanelUnroll * 2;
     __shared__ int2 staged[kWarpsPerBlock][32];          // {column id, value bits} of the current batch
     int2 *stage = staged[threadIdx.x >> 5];
@@ -390,7 +473,7 @@ spmm_panel_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
     uint64_t base64 = reinterpret_cast<uint64_t>(base);
     asm volatile("" : "+l"(base64));
     auto gather = [&](int col) {
-        return gather16<KEEP>(reinterpret_cast<const void *>(base64 + (uint64_t)(uint32_t)col * 256u), policy);   // n_cols < 2^24
+        return __ldg(reinterpret_cast<const float4 *>(base64 + (uint64_t)(uint32_t)col * 256u));   // n_cols < 2^24
     };
     int batch = 0;                                        // first nonzero (relative) of the staged batch
     int2 ahead = fetch(32);
@@ -482,12 +565,8 @@ static int launch_panels(const int64_t *rowptr, const int32_t *colidx, const flo
     const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
     GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
     const bool stream_c = (flags & SPMM_STREAM_C) && aligned(C, 16) && ldc % 4 == 0;
-    if (flags & SPMM_KEEP_B)
-        spmm_panel_kernel<true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k,
-                                                                              alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c);
-    else
-        spmm_panel_kernel<false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k,
-                                                                               alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c);
+    spmm_panel_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(rowptr, colidx, vals, n_rows, nnz, panels, n_cols, k, alpha, C,
+                                                                    ldc, chunk, n_chunks, n_tiles, stream_c);
     GNNGP_LAUNCHED();
     return GNNGP_OK;
 }
@@ -607,6 +686,9 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
     if (tw == 0) tw = ((double)n_cols * 128 * sizeof(float) <= 40.0 * 1024 * 1024) ? 128 : 64;
     if (vec == 2 && tw > 64) tw = 64;
     if (vec == 1) tw = 32;
+    const bool short_rows = (flags & SPMM_SHORT_ROWS) && vec == 4 && nnz < 64 * n_rows && k >= kShortTile &&
+                            (tile_cols == 0 || tile_cols == kShortTile);
+    if (short_rows) tw = kShortTile;
 
     // small graphs: shrink work items until the tile-0 wave covers the SMs a few times
     while (nnz_per_warp <= 0 && chunk > 32 && ceil_div(nnz, chunk) * ceil_div(k, tw) < (int64_t)sm_count() * 32) chunk >>= 1;
@@ -614,11 +696,17 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
     const int64_t k_full = (k / tw) * tw;
     int rc = zero_fill(rowptr, n_rows, chunk, C, ldc, k, flags, st);
     if (rc != GNNGP_OK) return rc;
-    const bool stream_c = (flags & SPMM_STREAM_C) != 0, keep = (flags & SPMM_KEEP_B) != 0;
-    if (k_full > 0) {
-        if (vec == 4 && tw == 128 && keep) rc = launch<4, 1, false, true>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
-        else if (vec == 4 && tw == 64 && keep) rc = launch<4, 2, false, true>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
-        else if (vec == 4 && tw == 128) rc = launch<4, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
+    const bool stream_c = (flags & SPMM_STREAM_C) != 0;
+    if (k_full > 0 && short_rows) {
+        const int64_t n_tiles = k_full / kShortTile, n_chunks = ceil_div(nnz, chunk);
+        const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
+        GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
+        const bool vec_c = aligned(C, 16) && ldc % 4 == 0;
+        spmm_short_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
+        GNNGP_LAUNCHED();
+    } else if (k_full > 0) {
+        if (vec == 4 && tw == 128) rc = launch<4, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
         else if (vec == 4 && tw == 64) rc = launch<4, 2, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);
         else if (vec == 4 && tw == 32) rc = launch<2, 2, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);
         else if (vec == 2 && tw == 64) rc = launch<2, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st);

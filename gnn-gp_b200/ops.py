@@ -66,6 +66,8 @@ class CudaOps(object):
         self.spmm_nnz_per_warp = 0
         # GNNGP_SPMM_PANELS = 1 / 0 forces / forbids the 64-column panel copy of the gathered operand (default: by shape)
         self.spmm_panels_mode = os.environ.get("GNNGP_SPMM_PANELS", "auto")
+        self.spmm_flags = int(self.lib.query("gnngp_spmm_set_flags", 0))     # read the library's setting ...
+        self.lib.query("gnngp_spmm_set_flags", self.spmm_flags)              # ... and put it back
         self.spmm_kernel_by_k = {}    # operand width -> name of the kernel the last product of that width ran (bench roofline)
 
     # ------------------------------------------------------------------ plumbing
@@ -148,7 +150,9 @@ class CudaOps(object):
         return int(self.lib.query("gnngp_set_gemm_engine", int(engine)))
 
     def set_spmm_flags(self, flags: int) -> int:
-        """Cache-behaviour flags of the SpMM kernels (``gnngp_spmm_set_flags``); returns the previous setting."""
+        """Tuning flags of the SpMM kernels (``gnngp_spmm_set_flags``: 1 streaming 16-byte stores, 2 zero-fill of cut /
+        empty rows only, 4 short-row kernel); returns the previous setting."""
+        self.spmm_flags = int(flags) & 7
         return int(self.lib.query("gnngp_spmm_set_flags", int(flags)))
 
     # ------------------------------------------------------------------ adjacency
@@ -326,7 +330,10 @@ class CudaOps(object):
             padded = self.empty(B.shape[0], k, B.device)
             padded.copy_(B)
             B, ldb = padded, self._ld(padded)
-        self.spmm_kernel_by_k[int(k)] = "spmm_panel_kernel" if use_panels else "spmm_csr_kernel"
+        short_rows = (not use_panels and self.spmm_flags & 4 and csr.nnz < 64 * csr.n_rows and k >= 128
+                      and int(self.spmm_tile_cols) in (0, 128) and ldb % 4 == 0 and B.data_ptr() % 16 == 0)
+        self.spmm_kernel_by_k[int(k)] = ("spmm_panel_kernel" if use_panels else
+                                         "spmm_short_rows_kernel" if short_rows else "spmm_csr_kernel")
         self.lib.call("gnngp_spmm_csr_f32", csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.vals.data_ptr(),
                       csr.n_rows, csr.n_cols, csr.nnz, B.data_ptr(), ldb, k, float(alpha), out.data_ptr(),
                       self._ld(out), int(self.spmm_tile_cols), int(self.spmm_nnz_per_warp), wptr, need, self._stream())

@@ -94,11 +94,12 @@ def test_spmm_tiles_alignment_and_strided_output(ops, ref, tile, chunk):
         ops.spmm_tile_cols, ops.spmm_nnz_per_warp = 0, 0
 
 
-@pytest.mark.parametrize("flags", [1, 2, 4, 7])
-def test_spmm_cache_flags_do_not_change_results(ops, ref, flags):
-    """gnngp_spmm_set_flags only changes cache behaviour and which rows are zero-filled: every flag combination
-    must reproduce the default kernels on a graph with a hub row, cut rows and empty rows, on both gather paths,
-    aligned and misaligned outputs, and must not leave a row of a garbage-filled output untouched."""
+@pytest.mark.parametrize("flags", [1, 2, 3, 4, 7])
+def test_spmm_tuning_flags_do_not_change_results(ops, ref, flags):
+    """gnngp_spmm_set_flags only changes store width, which rows are zero-filled and which kernel walks short rows:
+    every flag combination must reproduce the plain kernels (flags 0) on a graph with a hub row, cut rows and empty
+    rows and on a short-row graph, on both gather paths, aligned and misaligned outputs, and must not leave a row of
+    a garbage-filled output untouched."""
     n = 4000
     row, col, val = rand_graph(n, 300000, seed=17, hub=29, empty_rows=(0, 1, 2, 777, n - 1))
     csr = ops.csr_from_coo(row.cuda(), col.cuda(), val.cuda(), n, n)
@@ -106,10 +107,11 @@ def test_spmm_cache_flags_do_not_change_results(ops, ref, flags):
     short_row, short_col, short_val = rand_graph(n, 9 * n, seed=18, empty_rows=(5, 6, n - 2))
     short = ops.csr_from_coo(short_row.cuda(), short_col.cuda(), short_val.cuda(), n, n)
     short_ref = ref.csr_from_coo(short_row, short_col, short_val, n, n)
+    previous = ops.set_spmm_flags(0)
     try:
         for matrix, mref in ((csr, cref), (short, short_ref)):
             for k, lead, shift, tile, chunk in ((320, 320, 0, 0, 0), (321, 324, 4, 0, 64), (256, 256, 0, 64, 0), (130, 136, 4, 128, 32),
-                                                 (320, 323, 1, 0, 0), (77, 80, 0, 32, 0)):
+                                                 (320, 323, 1, 0, 0), (77, 80, 0, 32, 0), (256, 260, 0, 128, 512), (384, 384, 0, 0, 2048)):
                 g = torch.Generator().manual_seed(k + lead)
                 b = torch.randn(n, k, generator=g)
                 ops.spmm_tile_cols, ops.spmm_nnz_per_warp = tile, chunk
@@ -124,7 +126,7 @@ def test_spmm_cache_flags_do_not_change_results(ops, ref, flags):
                 assert rel(results[1], results[0]) < 1e-6, (flags, k, lead, shift, tile, chunk)
                 assert rel(results[1], ref.spmm(mref, b, 0.9)) < TOL
     finally:
-        ops.set_spmm_flags(0)
+        ops.set_spmm_flags(previous)
         ops.spmm_tile_cols, ops.spmm_nnz_per_warp = 0, 0
 
 
