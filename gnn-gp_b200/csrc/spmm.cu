@@ -35,8 +35,8 @@
 
 namespace gnngp {
 
-enum : int { SPMM_STREAM_C = 1, SPMM_ZERO_CUT_ROWS = 2, SPMM_SHORT_ROWS = 4, SPMM_ALL_FLAGS = 7 };
-static std::atomic<int> g_spmm_flags{SPMM_STREAM_C | SPMM_ZERO_CUT_ROWS};
+enum : int { SPMM_STREAM_C = 1, SPMM_ZERO_CUT_ROWS = 2, SPMM_SHORT_ROWS = 4, SPMM_SHORT_DEEP = 8, SPMM_ALL_FLAGS = 15 };
+static std::atomic<int> g_spmm_flags{SPMM_STREAM_C | SPMM_ZERO_CUT_ROWS | SPMM_SHORT_ROWS};
 
 // Rows that are not written by exactly one work item: cut by a border of the nnz-balanced split (their pieces
 // are combined with atomics) or empty (never visited).  One warp per row.
@@ -227,10 +227,12 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
 // the running row accumulator in nonzero order, and a row is flushed when the position reaches its end.  Row
 // ends come from a per-warp register cache of the next 32 row pointers (one coalesced load per 32 rows, read
 // with a shuffle).  One warp = one nonzero per gather instruction, 128 columns (16 bytes per lane).
-constexpr int kShortUnroll = 4;
 constexpr int kShortTile = 128;
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// kShortUnroll gathers (512 bytes each, one nonzero) are in flight per warp: the launch is bound by
+// bytes-in-flight / L2 latency (4 per warp x 32 warps = 64 KB per SM gave 8.0 TB/s of gathers at the arxiv shape).
+template <int kShortUnroll, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MIN_BLOCKS)
 spmm_short_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                        const float *__restrict__ vals, int64_t n_rows, int64_t nnz, const float *__restrict__ B,
                        int64_t ldb, float alpha, float *__restrict__ C, int64_t ldc, int64_t chunk, int64_t n_chunks,
@@ -702,8 +704,12 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
         const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
         GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
         const bool vec_c = aligned(C, 16) && ldc % 4 == 0;
-        spmm_short_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-            rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
+        if (flags & SPMM_SHORT_DEEP)
+            spmm_short_rows_kernel<8, 4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+                rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
+        else
+            spmm_short_rows_kernel<4, 1><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+                rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
         GNNGP_LAUNCHED();
     } else if (k_full > 0) {
         if (vec == 4 && tw == 128) rc = launch<4, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);

@@ -68,13 +68,14 @@ int gnngp_csr_from_coo(const int64_t *row, const int64_t *col, const float *val,
  * nnz_per_warp: nonzeros per warp work item (0 = default: 512, or 1024 on graphs with >= 2^25 nonzeros).  Rows that straddle a work item are
  * combined with fp32 atomics, so those rows of C are zero-filled first (the call does that itself). */
 size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k);
-/* Tuning flags of the SpMM kernels (results do not depend on them); returns the previous setting.  Default 3.
+/* Tuning flags of the SpMM kernels (results do not depend on them); returns the previous setting.  Default 7.
  * 1: rows written by a single work item leave with one 16-byte streaming store per lane (when C's rows are
  *    16-byte aligned) instead of four 4-byte stores;
  * 2: only rows that are accumulated with atomics (cut by a work-item border) or empty are zero-filled,
  *    instead of the whole C;
  * 4: graphs with fewer than 64 nonzeros per row on average take the short-row kernel of the row-major path
- *    (gathers issued four nonzeros at a time across row boundaries, 128-column tiles). */
+ *    (gathers issued four nonzeros at a time across row boundaries, 128-column tiles);
+ * 8: that kernel keeps eight gathers in flight per lane instead of four. */
 int gnngp_spmm_set_flags(int flags);
 int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals,
                        int64_t n_rows, int64_t n_cols, int64_t nnz, const float *B, int64_t ldb,

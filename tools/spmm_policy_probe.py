@@ -83,8 +83,10 @@ def main():
             for tile in tiles:
                 if tile and layout == "1":
                     continue
-                for flags in range(8):
+                for flags in range(16):
                     if (tile or layout == "1") and flags not in (0, 3):
+                        continue
+                    if flags >= 8 and (csr.nnz >= 64 * n or not flags & 4):     # flag 8 only modifies the short-row kernel
                         continue
                     ops.spmm_panels_mode, ops.spmm_tile_cols = layout, tile
                     ops.set_spmm_flags(flags)
