@@ -35,7 +35,7 @@
 
 namespace gnngp {
 
-enum : int { SPMM_STREAM_C = 1, SPMM_ZERO_CUT_ROWS = 2, SPMM_SHORT_ROWS = 4, SPMM_SHORT_DEEP = 8, SPMM_ALL_FLAGS = 15 };
+enum : int { SPMM_STREAM_C = 1, SPMM_ZERO_CUT_ROWS = 2, SPMM_SHORT_ROWS = 4, SPMM_ALL_FLAGS = 7 };
 static std::atomic<int> g_spmm_flags{SPMM_STREAM_C | SPMM_ZERO_CUT_ROWS | SPMM_SHORT_ROWS};
 
 // Rows that are not written by exactly one work item: cut by a border of the nnz-balanced split (their pieces
@@ -229,8 +229,11 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
 // with a shuffle).  One warp = one nonzero per gather instruction, 128 columns (16 bytes per lane).
 constexpr int kShortTile = 128;
 
-// kShortUnroll gathers (512 bytes each, one nonzero) are in flight per warp: the launch is bound by
-// bytes-in-flight / L2 latency (4 per warp x 32 warps = 64 KB per SM gave 8.0 TB/s of gathers at the arxiv shape).
+// kShortUnroll gathers (512 bytes each, one nonzero) are in flight per warp.  Measured at the arxiv shape (k = 9 200,
+// profiles/r2/call30_*): <4, 1> 11.6 ms, <8, 4> (eight in flight, 64 registers) 12.5 ms — the launch is not short of
+// loads in flight but of L2 hits: `ncu --set full` shows 38 % L2 hit rate and 52 GB of DRAM traffic (4.8 TB/s, 73 % of
+// the measured copy bandwidth) for 12.3 GB of algorithmic bytes, because the 87 MB of 128-column strips of one tile
+// pass, needed by the SMs of both dies, do not stay in the 126 MB L2.
 template <int kShortUnroll, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MIN_BLOCKS)
 spmm_short_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
@@ -704,12 +707,8 @@ extern "C" int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, 
         const int64_t blocks = ceil_div(n_tiles * n_chunks, kWarpsPerBlock);
         GNNGP_REQUIRE(blocks < ((int64_t)1 << 31), "spmm: grid of %lld blocks is too large", (long long)blocks);
         const bool vec_c = aligned(C, 16) && ldc % 4 == 0;
-        if (flags & SPMM_SHORT_DEEP)
-            spmm_short_rows_kernel<8, 4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-                rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
-        else
-            spmm_short_rows_kernel<4, 1><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-                rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
+        spmm_short_rows_kernel<4, 1><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            rowptr, colidx, vals, n_rows, nnz, B, ldb, alpha, C, ldc, chunk, n_chunks, n_tiles, stream_c && vec_c, vec_c);
         GNNGP_LAUNCHED();
     } else if (k_full > 0) {
         if (vec == 4 && tw == 128) rc = launch<4, 1, false>(rowptr, colidx, vals, n_rows, nnz, B, ldb, 0, k_full, alpha, C, ldc, chunk, st, stream_c);

@@ -151,8 +151,8 @@ class CudaOps(object):
 
     def set_spmm_flags(self, flags: int) -> int:
         """Tuning flags of the SpMM kernels (``gnngp_spmm_set_flags``: 1 streaming 16-byte stores, 2 zero-fill of cut /
-        empty rows only, 4 short-row kernel, 8 its deeper gather queue); returns the previous setting."""
-        self.spmm_flags = int(flags) & 15
+        empty rows only, 4 short-row kernel); returns the previous setting."""
+        self.spmm_flags = int(flags) & 7
         return int(self.lib.query("gnngp_spmm_set_flags", int(flags)))
 
     # ------------------------------------------------------------------ adjacency

@@ -74,8 +74,7 @@ size_t gnngp_spmm_workspace_bytes(int64_t n_cols, int64_t k);
  * 2: only rows that are accumulated with atomics (cut by a work-item border) or empty are zero-filled,
  *    instead of the whole C;
  * 4: graphs with fewer than 64 nonzeros per row on average take the short-row kernel of the row-major path
- *    (gathers issued four nonzeros at a time across row boundaries, 128-column tiles);
- * 8: that kernel keeps eight gathers in flight per lane instead of four. */
+ *    (gathers issued four nonzeros at a time across row boundaries, 128-column tiles). */
 int gnngp_spmm_set_flags(int flags);
 int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float *vals,
                        int64_t n_rows, int64_t n_cols, int64_t nnz, const float *B, int64_t ldb,

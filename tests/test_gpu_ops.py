@@ -94,7 +94,7 @@ def test_spmm_tiles_alignment_and_strided_output(ops, ref, tile, chunk):
         ops.spmm_tile_cols, ops.spmm_nnz_per_warp = 0, 0
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3, 4, 7, 15])
+@pytest.mark.parametrize("flags", [1, 2, 3, 4, 6])
 def test_spmm_tuning_flags_do_not_change_results(ops, ref, flags):
     """gnngp_spmm_set_flags only changes store width, which rows are zero-filled and which kernel walks short rows:
     every flag combination must reproduce the plain kernels (flags 0) on a graph with a hub row, cut rows and empty

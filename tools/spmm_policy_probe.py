@@ -2,7 +2,8 @@
 and both gather layouts, at the arxiv shape (short rows: the HBM-bound regime of SURVEY §8d) and the Reddit shape
 (dense rows: the L2-gather-bound regime).  Every variant is checked against the plain kernels' result (flags 0) before it is
 timed.  (The first run of this probe, profiles/r2/call28_*, still had an L2 evict_last flag on the gathers — flag 2 there, no
-effect at either shape, removed since — and numbered the zero-fill flag 4.)
+effect at either shape, removed since — and numbered the zero-fill flag 4; the third, call30_*, had a flag 8 that gave the
+short-row kernel eight gathers in flight instead of four: slower, removed.)
 
     python tools/spmm_policy_probe.py [out.json] [--shapes arxiv:9200,reddit:3052,reddit:15404]
 
@@ -83,10 +84,8 @@ def main():
             for tile in tiles:
                 if tile and layout == "1":
                     continue
-                for flags in range(16):
+                for flags in range(8):
                     if (tile or layout == "1") and flags not in (0, 3):
-                        continue
-                    if flags >= 8 and (csr.nnz >= 64 * n or not flags & 4):     # flag 8 only modifies the short-row kernel
                         continue
                     ops.spmm_panels_mode, ops.spmm_tile_cols = layout, tile
                     ops.set_spmm_flags(flags)
