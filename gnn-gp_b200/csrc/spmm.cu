@@ -397,8 +397,8 @@ __global__ void panelize_kernel(const float *__restrict__ B, int64_t ldb, int64_
 }
 
 // Fused all-gather + layout transform for the row-sharded mode: every rank pulls the row blocks of the
-// operand straight out of its peers' memory (NVLink P2P loads through pointers exchanged with torch
-// symmetric memory) and writes them into its local 64-column panels — one kernel instead of an NCCL
+// operand straight out of its peers' memory (NVLink P2P loads from the gnngp_exchange_* buffers the peers
+// mapped through CUDA IPC) and writes them into its local 64-column panels — one kernel instead of an NCCL
 // all-gather into a staging buffer followed by the panel copy.  peer[r] is rank r's [rows_per_rank x ld] block.
 __global__ void panelize_peers_kernel(const float *const *__restrict__ peer, int64_t rows_per_rank, int64_t ld, int64_t n,
                                       int64_t k, int64_t n_tiles, float *__restrict__ P)

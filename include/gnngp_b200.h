@@ -84,7 +84,7 @@ int gnngp_spmm_csr_f32(const int64_t *rowptr, const int32_t *colidx, const float
 /* Row-sharded mode: the same product with the operand already laid out as 64-column panels
  * ([ceil(k/64)][n_cols][64] floats, gnngp_spmm_workspace_bytes(n_cols, k) bytes), and the kernel that builds
  * those panels by pulling each rank's [rows_per_rank x ld] row block out of peer memory over NVLink
- * (peer_ptrs_dev: device array of `world` device pointers, e.g. torch symmetric memory's buffer_ptrs_dev).
+ * (peer_ptrs_dev: device array of `world` device pointers — the gnngp_exchange_* buffers below, mapped by CUDA IPC).
  * Together they replace "NCCL all-gather of the factor rows, then A_r @ X" (SURVEY.md section 8e). */
 int gnngp_panelize_peers_f32(const void *peer_ptrs_dev, int world, int64_t rows_per_rank, int64_t ld, int64_t n,
                              int64_t k, float *panels, gnngp_stream_t stream);
