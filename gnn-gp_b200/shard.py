@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import os
 import warnings
-from typing import Optional, Union
+from typing import Union
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,6 @@ and the golden fixtures), the Reddit shape on the GPU.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional
 
 import torch

@@ -20,7 +20,7 @@ from __future__ import annotations
 import ctypes
 import math
 import os
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 import scipy.sparse as sp
